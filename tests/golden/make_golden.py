@@ -1,0 +1,163 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on seeded
+synthetic checkpoints and inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The fixtures pin the oracle (tests/test_oracle_golden.py) and, on the GPU box, the CUDA engine.
+Checkpoints/inputs are regenerated from seeds by talkshow_b200/synth.py (uniform-only arithmetic,
+host independent); the fixtures store the small inputs, the outputs and fingerprints.
+"""
+import argparse
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import torch  # noqa: E402
+
+from ref_import import import_reference  # noqa: E402
+from talkshow_b200 import synth  # noqa: E402
+
+SAMPLER_SEED = 2024
+
+
+def draw_noise(steps, B, K=2048):
+    """The reference consumes one ``exponential_`` of shape [B,K] per sampled position
+    (gated_pixelcnn_v2.py:175 -> ATen multinomial)."""
+    out = torch.empty(steps, B, K)
+    for s in range(steps):
+        out[s] = torch.empty(B, K).exponential_(1)
+    return out
+
+
+def noise_fp(noise):
+    return np.array([float(noise.double().sum()), float(noise[0, 0, :8].double().sum()),
+                     float(noise[-1, -1, -8:].double().sum())])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    cwd = os.getcwd()
+    nets = import_reference()
+    import nets.smplx_body_pixel as ref_bp
+    import nets.smplx_body_vq as ref_vq
+    import nets.smplx_face as ref_face
+    from trainer.config import load_JsonConfig
+    torch.set_grad_enabled(False)
+
+    tmp = tempfile.mkdtemp()
+    vq_ckpt = synth.body_vq_checkpoint(0)
+    vq_path = os.path.join(tmp, "vq.pth")
+    torch.save({"generator": vq_ckpt}, vq_path)
+    bp_ckpt = synth.body_pixel_checkpoint(0)
+    face_ckpt = synth.face_checkpoint(0)
+
+    cfg_pixel = load_JsonConfig("config/body_pixel.json")
+    cfg_pixel.Model.vq_path = vq_path
+    cfg_vq = load_JsonConfig("config/body_vq.json")
+    cfg_face = load_JsonConfig("config/face.json")
+    a = types.SimpleNamespace(gpu="cpu", infer=True)
+
+    def want(n):
+        return not args.only or n in args.only.split(",")
+
+    out = {}
+
+    # ---- body pixel: wrapper end to end (config 3) ------------------------------------------
+    if want("pixel_b1_t30") or want("pixel_b3_t75") or want("pixel_cont"):
+        g = ref_bp.TrainWrapper(a, cfg_pixel)
+        g.load_state_dict(bp_ckpt)            # demo.py:54-62 passes ckpt['generator'] = this dict
+    if want("pixel_b1_t30"):
+        mfcc = synth.synth_mfcc(1, 120)       # [1,64,120]
+        ref_bp.get_mfcc_ta = lambda *aa, **kk: mfcc[0].transpose(0, 1).numpy()     # (M,64) like utils.py:177
+        torch.manual_seed(SAMPLER_SEED)
+        pred = g.infer_on_audio("synthetic.wav", id=torch.tensor([0]), fps=30, B=1)  # (1,120,129)
+        torch.manual_seed(SAMPLER_SEED)
+        noise = draw_noise(60, 1)
+        # codes: recompute through the same modules with the same seed
+        torch.manual_seed(SAMPLER_SEED)
+        audio = g.audioencoder(mfcc).unsqueeze(-1).repeat(1, 1, 1, 2)
+        lat = g.generator.generate(torch.tensor([0]), shape=[30, 2], batch_size=1, aud_feat=audio)
+        logits = g.generator(lat, torch.tensor([0]), audio)                       # teacher-forced [1,2048,30,2]
+        rows = [0, 1, 2, 3, 17, 18, 29]
+        np.savez_compressed(os.path.join(HERE, "pixel_b1_t30.npz"), mfcc=mfcc.numpy(), label=np.array([0]),
+                            audio=audio[..., 0].numpy(), codes=lat.numpy(), pred=pred,
+                            logit_rows=np.array(rows), logits=logits[0][:, rows, :].numpy(),
+                            noise_fp=noise_fp(noise), sampler_seed=SAMPLER_SEED,
+                            fp=np.array(list(synth.fingerprint(bp_ckpt).values())),
+                            fp_vq=np.array(list(synth.fingerprint(vq_ckpt).values())))
+        print("pixel_b1_t30", lat[0, :6].tolist(), pred.shape)
+
+    if want("pixel_b3_t75"):
+        mfcc = synth.synth_mfcc(3, 300, seed=77)
+        label = torch.tensor([0, 1, 3])
+        torch.manual_seed(SAMPLER_SEED + 1)
+        audio = g.audioencoder(mfcc).unsqueeze(-1).repeat(1, 1, 1, 2)
+        lat = g.generator.generate(label, shape=[75, 2], batch_size=3, aud_feat=audio)
+        body, _ = g.g_body.decode(b=3, w=75, latents=lat[..., 0])
+        hand, _ = g.g_hand.decode(b=3, w=75, latents=lat[..., 1])
+        pred = torch.cat([body, hand], 1).transpose(1, 2).numpy()
+        torch.manual_seed(SAMPLER_SEED + 1)
+        noise = draw_noise(150, 3)
+        np.savez_compressed(os.path.join(HERE, "pixel_b3_t75.npz"), label=label.numpy(), codes=lat.numpy(),
+                            pred=pred[:, ::7].copy(), pred_stride=7, noise_fp=noise_fp(noise),
+                            sampler_seed=SAMPLER_SEED + 1, mfcc_seed=77)
+        print("pixel_b3_t75", lat[:, :3].tolist())
+
+    if want("pixel_cont"):
+        # continuity path: generate(pre_latents, pre_audio), gated_pixelcnn_v2.py:158-165
+        mfcc = synth.synth_mfcc(2, 160, seed=99)
+        label = torch.tensor([2, 1])
+        audio = g.audioencoder(mfcc).unsqueeze(-1).repeat(1, 1, 1, 2)             # [2,256,40,2]
+        torch.manual_seed(SAMPLER_SEED + 2)
+        lat0 = g.generator.generate(label, shape=[15, 2], batch_size=2, aud_feat=audio[:, :, :15])
+        lat1 = g.generator.generate(label, shape=[25, 2], batch_size=2, aud_feat=audio[:, :, 15:],
+                                    pre_latents=lat0, pre_audio=audio[:, :, :15])
+        torch.manual_seed(SAMPLER_SEED + 2)
+        noise = draw_noise(80, 2)
+        np.savez_compressed(os.path.join(HERE, "pixel_cont.npz"), label=label.numpy(), codes0=lat0.numpy(),
+                            codes1=lat1.numpy(), noise_fp=noise_fp(noise), sampler_seed=SAMPLER_SEED + 2,
+                            mfcc_seed=99)
+        print("pixel_cont", lat1[:, :3].tolist())
+
+    # ---- VQ roundtrip (config 2) -------------------------------------------------------------
+    if want("vq_roundtrip"):
+        gv = ref_vq.TrainWrapper(a, cfg_vq)
+        gv.load_state_dict(vq_ckpt)
+        poses = synth.synth_poses(2, 88)
+        outv = gv.infer_on_audio(torch.zeros(2, 64, 88), initial_pose=poses, fps=30)     # (88, 129)
+        gt = poses[:, gv.c_index].permute(0, 2, 1)
+        eb, ib = gv.g_body.encode(gt_poses=gt[..., :39])
+        eh, ih = gv.g_hand.encode(gt_poses=gt[..., 39:])
+        np.savez_compressed(os.path.join(HERE, "vq_roundtrip.npz"), poses=poses.numpy(), out=outv,
+                            idx_body=ib.numpy(), idx_hand=ih.numpy(), e_body=eb.numpy(),
+                            fp_vq=np.array(list(synth.fingerprint(vq_ckpt).values())))
+        print("vq_roundtrip", ib.tolist(), outv.shape)
+
+    # ---- face (config 1 stand-in + batch) ----------------------------------------------------
+    if want("face"):
+        gf = ref_face.TrainWrapper(a, cfg_face)
+        gf.load_state_dict(face_ckpt)
+        wave = synth.synth_wave(1, 64000)
+        o1 = gf.infer_on_audio(wave[:, None, :])                                       # (1,120,103), id=None
+        wave2 = synth.synth_wave(2, 24000, seed=5)
+        ids = torch.tensor([1, 3])
+        o2 = gf.generator(wave2[:, None, :], None, torch.nn.functional.one_hot(ids, 4), time_steps=45)[0].numpy()
+        np.savez_compressed(os.path.join(HERE, "face.npz"), out_4s=o1, out_b2=o2, ids_b2=ids.numpy(),
+                            wave_head=wave[0, :64].numpy(),
+                            fp=np.array(list(synth.fingerprint(face_ckpt).values())))
+        print("face", o1.shape, float(np.abs(o1).max()), o2.shape)
+    os.chdir(cwd)
+
+
+if __name__ == "__main__":
+    main()
