@@ -1,0 +1,123 @@
+/* talkshow_b200 — C ABI of the B200-native TalkSHOW speech-to-motion engine.
+ *
+ * The reference (yhw-yhw/TalkSHOW) is pure Python/PyTorch and has no FFI of its own; the boundary
+ * this library replaces is the *module level* of nets/spg/ — the calls the wrappers
+ * nets/smplx_body_pixel.py, nets/smplx_body_vq.py and nets/smplx_face.py make.  Each entry point
+ * below cites the reference call it replaces.  The host-side mirror of the wrappers lives in
+ * talkshow_b200/nets/ (ctypes binding: talkshow_b200/_lib.py).
+ *
+ * Conventions
+ *  - every function returns 0 (TS_OK) on success, a ts_status otherwise; ts_last_error() gives text;
+ *  - all data pointers are DEVICE pointers on the engine's device unless the name says `host`;
+ *    tensors are dense, fp32 / int64, in the reference's own layouts (channel-first [B,C,T]);
+ *  - caller owns inputs/outputs; the engine owns packed weights + workspace;
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation;
+ *  - one engine per device, not thread-safe.
+ */
+#ifndef TALKSHOW_B200_H
+#define TALKSHOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ts_engine ts_engine;
+
+enum ts_status {
+  TS_OK = 0,
+  TS_ERR_INVALID = 1,    /* bad argument / shape */
+  TS_ERR_NOT_LOADED = 2, /* weights for this module were not loaded */
+  TS_ERR_MISSING = 3,    /* a checkpoint tensor is missing or has the wrong shape */
+  TS_ERR_CUDA = 4,       /* CUDA runtime error */
+  TS_ERR_UNSUPPORTED = 5
+};
+
+/* One checkpoint tensor, HOST memory, fp32 (dtype 0) or int64 (dtype 1), dense row-major, named
+ * exactly as in the reference's state_dict() after 'module.' stripping
+ * (nets/smplx_body_pixel.py:117-126). */
+typedef struct ts_tensor {
+  const char* name;
+  const void* data;
+  int32_t dtype;
+  int32_t ndim;
+  int64_t shape[6];
+} ts_tensor;
+
+int ts_engine_create(ts_engine** out, int device);
+void ts_engine_destroy(ts_engine* e);
+const char* ts_last_error(ts_engine* e); /* e may be NULL: error of the last failed create */
+int ts_engine_sm_count(ts_engine* e);
+
+/* ---- weights: replace nn.Module.load_state_dict for each sub-module ------------------------ */
+/* GatedPixelCNN(2048, dim, n_layers, 4, audio=True, bh_model=True): nets/smplx_body_pixel.py:53,
+ * keys of ckpt['generator']['generator'].  dim/n_layers are read from the tensor shapes. */
+int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n);
+/* AudioEncoder(64,256,2,256): nets/smplx_body_pixel.py:46, ckpt['generator']['audioencoder']. */
+int ts_load_audioenc(ts_engine* e, const ts_tensor* tensors, int n);
+/* VQVAE(39|90,64,2048,1024,2,512): nets/smplx_body_pixel.py:54-62, which = 0 g_body, 1 g_hand. */
+int ts_load_vq(ts_engine* e, int which, const ts_tensor* tensors, int n);
+/* s2g_face.Generator: nets/smplx_face.py:37-45, ckpt['generator']['generator'].  The positional
+ * conv must be passed with its effective weight under
+ * 'audio_encoder.encoder.pos_conv_embed.conv.weight' [768,48,128] (the host shim resolves the
+ * weight_norm parametrisation). */
+int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n);
+
+/* ---- hot path ------------------------------------------------------------------------------- */
+/* AudioEncoder.forward, nets/spg/vqvae_1d.py:27-34.  mfcc [B,64,M] -> out [B,256,T],
+ * T = ts_latent_rows(M). */
+int ts_audio_encode(ts_engine* e, const float* mfcc, float* out, int B, int M, void* stream);
+int ts_latent_rows(int M);
+
+/* GatedPixelCNN.generate, nets/spg/gated_pixelcnn_v2.py:152-177, as an exact O(T) incremental
+ * evaluation.  aud [B,256,T0+T] (the AudioEncoder output, incl. the T0 prefix rows when
+ * pre_latents is given, :158-165), label [B] int64, noise [2T,B,2048] = the Exp(1) draws the
+ * reference's multinomial would consume, one [B,2048] block per sampled position in the order
+ * (i,0),(i,1) (RNG contract), pre_latents [B,T0,2] int64 or NULL (T0=0).
+ * idx_out [B,T,2] int64.  logits_out (may be NULL) [2T,B,2048]: the logits each draw used. */
+int ts_pixelcnn_generate(ts_engine* e, const float* aud, const int64_t* label, const float* noise,
+                         int64_t* idx_out, float* logits_out, int B, int T, const int64_t* pre_latents, int T0,
+                         void* stream);
+/* GatedPixelCNN.forward (teacher forced), :130-150, for rows [0,T): logits_out [B,2048,T,2]. */
+int ts_pixelcnn_logits(ts_engine* e, const float* aud, const int64_t* label, const int64_t* codes,
+                       float* logits_out, int B, int T, void* stream);
+
+/* VQVAE.decode(latents=...), nets/spg/vqvae_1d.py:201-208: idx [B,T] int64 -> out [B,C,4T]
+ * (C = 39 body / 90 hand). */
+int ts_vq_decode(ts_engine* e, int which, const int64_t* idx, float* out, int B, int T, void* stream);
+/* VQVAE.encode, :196-199: poses [B,F,C] -> idx [B,T] int64 (T=F/4), e_out (may be NULL) [B,64,T]. */
+int ts_vq_encode(ts_engine* e, int which, const float* poses, int64_t* idx, float* e_out, int B, int F,
+                 void* stream);
+
+/* s2g_face.Generator.forward, nets/spg/s2g_face.py:196-224: wave [B,N] (16 kHz), id [B,4] float
+ * one-hot (zeros = "no id", nets/smplx_face.py:205-206) -> out [B,frame,103]. */
+int ts_face_forward(ts_engine* e, const float* wave, const float* id, float* out, int B, int N, int frame,
+                    void* stream);
+
+/* s2g_body_pixel.infer_on_audio core, nets/smplx_body_pixel.py:270-285, fused:
+ * mfcc [B,64,M] -> codes [B,T,2] (may be NULL), poses [B,4T,129] (body 39 + hand 90). */
+int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise, int64_t* codes,
+                     float* poses, int B, int M, void* stream);
+
+/* scripts/demo.py:182-229 + data_utils/lower_body.py:68-87 (part2full): face [B,Ff,103],
+ * body [B,Fb,129] -> out [B,Ff,265]; body is padded with its last frame / truncated to Ff. */
+int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* out, int B, int Ff, int Fb,
+                     int stand, void* stream);
+
+/* ---- introspection (tests / bench) ---------------------------------------------------------- */
+/* number of kernel launches issued by this engine since creation */
+int64_t ts_launch_count(ts_engine* e);
+/* device time of the last ts_pixelcnn_generate persistent-kernel launch is measured by the caller
+ * with events; this returns the algorithmic weight bytes one latent row touches. */
+int64_t ts_pixelcnn_row_bytes(ts_engine* e);
+/* Export the PixelCNN execution plan (stage table + packed weight blob) to host buffers so a test
+ * can interpret it on the CPU; sizes are returned when the buffers are NULL. */
+int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len);
+/* 0 = persistent cooperative kernel (default), 1 = one launch per stage (debug cross-check) */
+int ts_set_pixelcnn_mode(ts_engine* e, int mode);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

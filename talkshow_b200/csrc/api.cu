@@ -1,0 +1,156 @@
+// talkshow_b200 — engine lifetime, error reporting, pose assembly, fused body path entry.
+#include "convstack.h"
+#include "pixelcnn.h"
+
+using namespace ts;
+
+static std::string g_create_err;
+
+float* ts_engine::upload(const std::vector<float>& h) {
+  if (host_only) return nullptr;
+  void* d = dmalloc(h.size() * sizeof(float));
+  TS_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return (float*)d;
+}
+void* ts_engine::dmalloc(size_t bytes) {
+  if (host_only) return nullptr;
+  void* d = nullptr;
+  TS_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
+  owned.push_back(d);
+  return d;
+}
+
+extern "C" int ts_engine_create(ts_engine** out, int device) {
+  if (!out) return TS_ERR_INVALID;
+  *out = nullptr;
+  ts_engine* e = new ts_engine();
+  try {
+    e->device = device;
+    if (device < 0) {  // host-only planning mode: weight packing / plan export without a GPU (tests)
+      e->host_only = true;
+      e->sm_count = -device > 1 ? -device : 148;
+    } else {
+      int n = 0;
+      TS_CUDA(cudaGetDeviceCount(&n));
+      if (device >= n) fail(TS_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+      TS_CUDA(cudaSetDevice(device));
+      cudaDeviceProp prop;
+      TS_CUDA(cudaGetDeviceProperties(&prop, device));
+      if (prop.major < 10) fail(TS_ERR_UNSUPPORTED, "talkshow_b200 needs an sm_100 (Blackwell) device, found sm_%d%d", prop.major, prop.minor);
+      e->sm_count = prop.multiProcessorCount;
+    }
+  } catch (const std::exception& ex) {
+    g_create_err = ex.what();
+    delete e;
+    return TS_ERR_CUDA;
+  }
+  *out = e;
+  return TS_OK;
+}
+
+extern "C" void ts_engine_destroy(ts_engine* e) {
+  if (!e) return;
+  if (!e->host_only) {
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (void* p : e->owned) cudaFree(p);
+    e->ws.buf.release();
+  }
+  delete e->pix;
+  delete e->conv;
+  ts::face_destroy(e);
+  delete e;
+}
+
+extern "C" const char* ts_last_error(ts_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+extern "C" int ts_engine_sm_count(ts_engine* e) { return e ? e->sm_count : 0; }
+extern "C" int64_t ts_launch_count(ts_engine* e) { return e ? e->launches : 0; }
+extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
+  if (!e || mode < 0 || mode > 1) return TS_ERR_INVALID;
+  e->pixel_mode = mode;
+  return TS_OK;
+}
+
+// ---- pose assembly: scripts/demo.py:182-229 + data_utils/lower_body.py:68-87 -------------------
+__constant__ float c_lower_pose[33] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 3.0747f, -0.0158f, -0.0152f,
+    -1.1826512813568115f, 0.23866955935955048f, 0.15146760642528534f, -1.2604516744613647f, -0.3160211145877838f,
+    -0.1603458970785141f, 1.1654603481292725f, 0.0f, 0.0f, 1.2521806955337524f, 0.041598282754421234f,
+    -0.06312154978513718f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+
+// out column -> source: pred = cat[jaw(3), body(129), expr(100)] (232), part2full inserts lower-pose
+// blocks: [pred 0:3 | lp 0:15 | pred 3:6 | lp 15:21 | pred 6:9 | lp 21:27 | pred 9:12 | lp 27:33 | pred 12:232]
+__global__ void assemble_kernel(const float* __restrict__ face, const float* __restrict__ body, float* __restrict__ out,
+                                int B, int Ff, int Fb, int stand) {
+  long n = (long)B * Ff * 265;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = i % 265;
+    long bf = i / 265;
+    int f = bf % Ff, b = bf / Ff;
+    int pc = -1, lp = -1;  // index into pred (232) or into lower pose (33)
+    if (c < 3) pc = c;
+    else if (c < 18) lp = c - 3;
+    else if (c < 21) pc = c - 15;
+    else if (c < 27) lp = c - 21 + 15;
+    else if (c < 30) pc = c - 21;
+    else if (c < 36) lp = c - 30 + 21;
+    else if (c < 39) pc = c - 27;
+    else if (c < 45) lp = c - 39 + 27;
+    else pc = c - 33;
+    float v;
+    if (lp >= 0) {
+      v = stand ? ((lp >= 6 && lp < 9) ? c_lower_pose[lp] : 0.f) : c_lower_pose[lp];
+    } else if (pc < 3) {
+      v = face[((long)b * Ff + f) * 103 + pc];
+    } else if (pc < 132) {
+      int fb = f < Fb ? f : Fb - 1;
+      v = body[((long)b * Fb + fb) * 129 + (pc - 3)];
+    } else {
+      v = face[((long)b * Ff + f) * 103 + 3 + (pc - 132)];
+    }
+    out[i] = v;
+  }
+}
+
+extern "C" int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* out, int B, int Ff, int Fb,
+                                int stand, void* stream) {
+  TS_API_BEGIN(e)
+  if (B <= 0 || Ff <= 0 || Fb <= 0) fail(TS_ERR_INVALID, "ts_assemble_pose: B=%d Ff=%d Fb=%d", B, Ff, Fb);
+  long n = (long)B * Ff * 265;
+  int blocks = (int)std::min<long>((n + 255) / 256, 148 * 8);
+  assemble_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(face, body, out, B, Ff, Fb, stand);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+  TS_API_END(e)
+}
+
+// ---- fused body path: audio encoder -> PixelCNN sampler -> two VQ decoders -------------------------
+extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise,
+                                int64_t* codes, float* poses, int B, int M, void* stream) {
+  TS_API_BEGIN(e)
+  if (!e->conv || !e->conv->audio_loaded) fail(TS_ERR_NOT_LOADED, "audio encoder weights not loaded");
+  if (!e->conv->vq[0].loaded || !e->conv->vq[1].loaded) fail(TS_ERR_NOT_LOADED, "vq weights not loaded");
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  if (B <= 0 || M < 4) fail(TS_ERR_INVALID, "ts_body_generate: B=%d M=%d", B, M);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int T = ts_latent_rows(M);
+  auto body = [&] {
+    Act3 x = new_act(e, B, M, 64, 1, s);
+    nct_to_act(e, mfcc, 64, x, s);
+    Act3 a = run_trunk(e, e->conv->audio, x, s);          // [B,T,256] channel-last, pad 1
+    int64_t* idx = e->ws.alloc<int64_t>((size_t)B * T * 2);
+    int64_t* idx_c = e->ws.alloc<int64_t>((size_t)B * T * 2);  // [2][B][T] column-split copy
+    pixelcnn_generate_act(e, a, label, noise, idx, nullptr, B, T, nullptr, 0, s);
+    split_codes(e, idx, idx_c, B, T, codes, s);
+    for (int w = 0; w < 2; ++w) {
+      Act3 y = run_vq_decode(e, e->conv->vq[w], idx_c + (size_t)w * B * T, B, T, s);
+      act_to_btc(e, y, e->conv->vq[w].out_dim, poses, 129, w ? 39 : 0, s);
+    }
+  };
+  e->ws.begin_sizing();
+  body();
+  size_t need = e->ws.need;
+  e->ws.buf.ensure(need + 256);
+  e->ws.begin(need);
+  body();
+  TS_API_END(e)
+}

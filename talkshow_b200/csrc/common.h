@@ -1,0 +1,152 @@
+// talkshow_b200 — shared host-side declarations (engine object, checkpoint lookup, workspace).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/talkshow_b200.h"
+
+namespace ts {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+[[noreturn]] inline void fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(code, buf);
+}
+
+#define TS_CUDA(x)                                                                              \
+  do {                                                                                          \
+    cudaError_t _e = (x);                                                                       \
+    if (_e != cudaSuccess) ts::fail(TS_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- checkpoint view -----------------------------------------------------------------------
+struct Ckpt {
+  std::map<std::string, const ts_tensor*> m;
+  Ckpt(const ts_tensor* t, int n) {
+    for (int i = 0; i < n; ++i) m[t[i].name] = &t[i];
+  }
+  bool has(const std::string& k) const { return m.count(k) != 0; }
+  // fp32 tensor with exactly this shape
+  const float* f32(const std::string& k, std::initializer_list<int64_t> shape) const {
+    auto it = m.find(k);
+    if (it == m.end()) fail(TS_ERR_MISSING, "checkpoint tensor '%s' missing", k.c_str());
+    const ts_tensor* t = it->second;
+    if (t->dtype != 0) fail(TS_ERR_MISSING, "checkpoint tensor '%s' is not fp32", k.c_str());
+    if (t->ndim != (int)shape.size()) fail(TS_ERR_MISSING, "checkpoint tensor '%s' has ndim %d", k.c_str(), t->ndim);
+    int i = 0;
+    for (int64_t d : shape) {
+      if (t->shape[i] != d) fail(TS_ERR_MISSING, "checkpoint tensor '%s' dim %d is %lld, expected %lld", k.c_str(), i,
+                                 (long long)t->shape[i], (long long)d);
+      ++i;
+    }
+    return (const float*)t->data;
+  }
+  const ts_tensor* get(const std::string& k) const {
+    auto it = m.find(k);
+    if (it == m.end()) fail(TS_ERR_MISSING, "checkpoint tensor '%s' missing", k.c_str());
+    return it->second;
+  }
+};
+
+// ---- device buffer owned by the engine ------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) TS_CUDA(cudaFree(p));
+    p = nullptr;
+    bytes = 0;
+    TS_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return (T*)p; }
+};
+
+// bump allocator over one DevBuf, reset at the start of every API call
+struct Workspace {
+  DevBuf buf;
+  size_t off = 0;
+  size_t need = 0;  // high-water mark of the sizing pass
+  bool sizing = false;
+  void begin_sizing() { sizing = true; off = 0; need = 0; }
+  void begin(size_t) { sizing = false; off = 0; }
+  template <class T>
+  T* alloc(size_t n) {
+    size_t b = (n * sizeof(T) + 255) & ~size_t(255);
+    size_t o = off;
+    off += b;
+    if (off > need) need = off;
+    if (sizing) return nullptr;
+    if (off > buf.bytes) fail(TS_ERR_CUDA, "workspace overflow (%zu > %zu)", off, buf.bytes);
+    return (T*)((char*)buf.p + o);
+  }
+};
+
+// A conv/linear layer packed for the generic GEMM: W [N][K] row-major on the device, K = taps*Cin
+// (tap-major, channel-minor, Cin padded to a multiple of 4), bias [N].
+struct Layer {
+  float* W = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0, taps = 1, cin = 0;  // cin = padded input channels
+};
+
+struct PixelPlan;  // pixelcnn.cu
+struct ConvStacks; // convstack.cu
+struct FaceNet;    // face.cu
+
+}  // namespace ts
+
+struct ts_engine {
+  int device = 0;
+  bool host_only = false;
+  int sm_count = 0;
+  std::string err;
+  int64_t launches = 0;
+  int pixel_mode = 0;
+  ts::PixelPlan* pix = nullptr;
+  ts::ConvStacks* conv = nullptr;
+  ts::FaceNet* face = nullptr;
+  ts::Workspace ws;
+  std::vector<void*> owned;  // device allocations holding packed weights
+  float* upload(const std::vector<float>& h);
+  void* dmalloc(size_t bytes);
+};
+
+// run `body`, convert exceptions to status codes
+#define TS_API_BEGIN(e) \
+  try {                 \
+    if (!(e)) return TS_ERR_INVALID;
+#define TS_API_END(e)                     \
+  return TS_OK;                           \
+  }                                       \
+  catch (const ts::Error& ex) {           \
+    (e)->err = ex.what();                 \
+    return ex.code;                       \
+  }                                       \
+  catch (const std::exception& ex) {      \
+    (e)->err = ex.what();                 \
+    return TS_ERR_INVALID;                \
+  }

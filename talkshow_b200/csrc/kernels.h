@@ -1,0 +1,66 @@
+// talkshow_b200 — device kernels shared by the conv stacks and the face network (host launchers).
+#pragma once
+#include "common.h"
+
+namespace ts {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_GELU = 3 };
+
+// Channel-last activation with explicit zero rows before/after every batch item:
+// element (b, t, c) lives at p[(b*(T+2*pad) + pad + t)*C + c].
+struct Act3 {
+  float* p = nullptr;
+  int B = 0, T = 0, C = 0, pad = 0;
+  __host__ __device__ long bstride() const { return (long)(T + 2 * pad) * C; }
+  __host__ __device__ float* row(int b, int t) const { return p + ((long)b * (T + 2 * pad) + pad + t) * C; }
+  __host__ __device__ size_t numel() const { return (size_t)B * (T + 2 * pad) * C; }
+};
+
+// C[m][n] = act( sum_k A(m,k) * W[n][k] + bias[n] + R(m,n) ), fp32 FFMA, fp32 accumulate.
+//   row m -> (b = m / mper, t = m % mper);  A(m,k) = A[b*a_bs + t*a_rs + (k/kc)*a_ts + k%kc]
+//   C(m,n) = C[b*c_bs + t*c_rs + n];  R likewise with r_bs/r_rs (R may be null)
+// gridDim.z = groups: A += g*a_goff, W += g*w_goff, bias += g*n_goff, C/R += g*n_goff.
+struct GemmP {
+  const float* A = nullptr;
+  const float* W = nullptr;
+  const float* bias = nullptr;
+  const float* R = nullptr;
+  float* C = nullptr;
+  int M = 0, N = 0, K = 0, mper = 1;
+  long a_bs = 0, a_rs = 0;
+  int kc = 0, a_ts = 0;
+  long c_bs = 0, c_rs = 0, r_bs = 0, r_rs = 0;
+  int act = 0, ldw = 0;
+  int groups = 1;
+  long a_goff = 0, w_goff = 0, n_goff = 0;
+};
+
+void launch_gemm(ts_engine* e, const GemmP& p, cudaStream_t s);
+
+// Conv1d (kernel k, stride s, zero padding p) as one GEMM over a padded channel-last input.
+// x.pad must be >= p.  Output (b,t,n) is written to y.row(b, t*y_tmul + y_toff)[n] so a transposed
+// conv can interleave its even/odd phases.  res (optional) is added before the activation and is
+// indexed like y with y_tmul/y_toff = 1/0.
+void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int p, const Act3& y, int T_out,
+            int act, const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int x_toff = 0);
+
+// [B,C,T] -> padded channel-last Act3 (pads and channel padding zeroed); and back.
+void nct_to_act(ts_engine* e, const float* in, int C, const Act3& out, cudaStream_t s);
+void btc_to_act(ts_engine* e, const float* in, int C, const Act3& out, cudaStream_t s);   // in [B,T,C]
+void act_to_nct(ts_engine* e, const Act3& in, int C, float* out, cudaStream_t s);          // out [B,C,T]
+void act_to_btc(ts_engine* e, const Act3& in, int C, float* out, int ldo, int ooff, cudaStream_t s);
+void zero_pads(ts_engine* e, const Act3& a, cudaStream_t s);
+
+// codebook gather: idx [B*T] int64 -> out rows (C = 64)
+void gather_rows(ts_engine* e, const float* table, int C, const int64_t* idx, const Act3& out, cudaStream_t s);
+// VectorQuantizerEMA.get_code_indices (vqvae_modules.py:311-319): z rows -> argmin index
+void vq_argmin(ts_engine* e, const float* codebook, const float* ee, int ncodes, const Act3& z, int64_t* idx,
+               cudaStream_t s);
+// row-wise LayerNorm over C, y = LN(x)*g+b (+res) then act; x,y,res channel-last with C channels
+void layernorm(ts_engine* e, const Act3& x, const float* g, const float* b, const Act3& y, const Act3* res, int act,
+               float eps, cudaStream_t s);
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int pad4(int c) { return (c + 3) & ~3; }
+
+}  // namespace ts

@@ -1,0 +1,829 @@
+// talkshow_b200 — gated PixelCNN prior sampled step by step, as an exact O(T) incremental
+// evaluation (reference: GatedPixelCNN.generate / forward / GatedMaskedConv2d.forward,
+// nets/spg/gated_pixelcnn_v2.py:61-87,130-177 — which re-runs the whole network over the whole
+// [T,2] grid for each of the 2T sampled positions).
+//
+// Design: one PERSISTENT cooperative kernel, one CTA per SM.  A latent row is a
+// fixed sequence of 84 dependent "stages" (16 vertical-stack, 2 x 34 horizontal-stack + output +
+// sample); in each stage every CTA owns a slice of the stage's OUTPUT CHANNELS for all samples of
+// the batch tile, so every weight byte is read exactly once per row per GPU.  The CTA's weight slice
+// for stage s+1 is pulled into shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier) while
+// stage s computes; activations live in an L2-resident arena laid out [channel][64 samples] and are
+// exchanged between CTAs through a release/acquire grid barrier.  All arithmetic is fp32 FFMA with a
+// fixed summation order (bit-reproducible run to run, independent of batch position).
+#include "pixelcnn.h"
+#include "convstack.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ts {
+
+// =============================================================================================
+// host: plan construction
+// =============================================================================================
+struct Job {
+  int epi, layer, col, nrows, K, ncol;
+  bool pairs;
+};
+
+static std::vector<std::vector<Job>> build_stages(int L) {
+  const int D = PIX_D;
+  std::vector<std::vector<Job>> st;
+  // ---- vertical pass -----------------------------------------------------------------------
+  st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});
+  for (int l = 1; l < L; ++l) {
+    std::vector<Job> j = {{EPI_VERT, l, 0, 2 * D, 4 * D, 1, true}, {EPI_VERT, l, 1, 2 * D, 4 * D, 1, true}};
+    if (l >= 2) j.push_back({EPI_V2H, l - 1, 0, 2 * D, 2 * D, 2, false});
+    st.push_back(j);
+  }
+  // ---- horizontal pass, column 0 then column 1 ------------------------------------------------
+  for (int c = 0; c < 2; ++c) {
+    std::vector<Job> j = {{EPI_HGATE, 0, c, 2 * D, c ? D : 0, 1, true}};
+    if (c == 0) j.push_back({EPI_V2H, L - 1, 0, 2 * D, 2 * D, 2, false});
+    st.push_back(j);
+    st.push_back({{EPI_HRES, 0, c, D, D, 1, false}});
+    st.push_back({{EPI_FUSEH, 0, c, D, D, 1, false}});
+    for (int l = 1; l < L; ++l) {
+      st.push_back({{EPI_HGATE, l, c, 2 * D, c ? 2 * D : D, 1, true}});
+      st.push_back({{EPI_HRES, l, c, D, D, 1, false}});
+    }
+    st.push_back({{EPI_OUT1, 0, c, 512, D, 1, false}});
+    st.push_back({{EPI_OUT2, 0, c, PIX_NCODE, 512, 1, false}});
+    st.push_back({{EPI_SAMPLE, 0, c, 0, 0, 1, false}});
+  }
+  return st;
+}
+
+static PixLayout make_layout(int L) {
+  PixLayout a;
+  int o = 0;
+  auto take = [&](int nseg) { int r = o; o += nseg * PIX_SEG; return r; };
+  a.E = take(4 * 2);
+  a.XV1P = take(2);
+  a.XV = take(L * 2 * 2);
+  a.HV = take(2 * 2 * 2);
+  a.V2H = take(L * 2 * 2);
+  a.G = take(1);
+  a.XHP = take(1);
+  a.XH = take(2 * (L + 1));
+  a.Y = take(2);
+  a.LOG = take(PIX_NCODE / PIX_D);
+  a.CLS = take(L * 2);
+  a.total = o;
+  return a;
+}
+
+// weight of output row `jr` (job row space) at reduction index k, and its bias
+struct WeightSrc {
+  const Ckpt& ck;
+  int L;
+  std::vector<const float*> vs, vsb, v2h, v2hb, hs, hsb, hr, hrb;
+  const float *fv, *fh, *o1, *o1b, *o2, *o2b;
+  WeightSrc(const Ckpt& c, int L_) : ck(c), L(L_) {
+    const int D = PIX_D;
+    for (int l = 0; l < L; ++l) {
+      std::string p = "layers." + std::to_string(l) + ".";
+      vs.push_back(ck.f32(p + "vert_stack.weight", {2 * D, D, l == 0 ? 4 : 2, 3}));
+      vsb.push_back(ck.f32(p + "vert_stack.bias", {2 * D}));
+      v2h.push_back(ck.f32(p + "vert_to_horiz.weight", {2 * D, 2 * D, 1, 1}));
+      v2hb.push_back(ck.f32(p + "vert_to_horiz.bias", {2 * D}));
+      hs.push_back(ck.f32(p + "horiz_stack.weight", {2 * D, D, 1, 2}));
+      hsb.push_back(ck.f32(p + "horiz_stack.bias", {2 * D}));
+      hr.push_back(ck.f32(p + "horiz_resid.weight", {D, D, 1, 1}));
+      hrb.push_back(ck.f32(p + "horiz_resid.bias", {D}));
+    }
+    fv = ck.f32("fusion_v.weight", {D, 2 * D, 1, 1});
+    fh = ck.f32("fusion_h.weight", {D, 2 * D, 1, 1});
+    o1 = ck.f32("output_conv.0.weight", {512, D, 1, 1});
+    o1b = ck.f32("output_conv.0.bias", {512});
+    o2 = ck.f32("output_conv.2.weight", {PIX_NCODE, 512, 1, 1});
+    o2b = ck.f32("output_conv.2.bias", {PIX_NCODE});
+  }
+  static int chan(const Job& j, int jr) { return j.pairs ? (jr & 1) * PIX_D + (jr >> 1) : jr; }
+  float w(const Job& j, int jr, int k) const {
+    const int D = PIX_D;
+    int ch = chan(j, jr), sidx = k / D, ci = k % D, l = j.layer;
+    switch (j.epi) {
+      case EPI_VERT0: {  // seg = kh*2 + input col; kw = input col - out col + 1   (Appendix C of SURVEY.md)
+        int kh = sidx >> 1, icol = sidx & 1, kw = icol - j.col + 1;
+        return vs[0][(((size_t)ch * D + ci) * 4 + kh) * 3 + kw];
+      }
+      case EPI_VERT: {
+        int kh = sidx >> 1, icol = sidx & 1, kw = icol - j.col + 1;
+        return vs[l][(((size_t)ch * D + ci) * 2 + kh) * 3 + kw];
+      }
+      case EPI_V2H: return v2h[l][(size_t)ch * 2 * D + k];
+      case EPI_FUSEV: return fv[(size_t)ch * 2 * D + k];
+      case EPI_FUSEH: return fh[(size_t)ch * 2 * D + k];
+      case EPI_HGATE: {
+        int tap;
+        if (l == 0) tap = 0;                 // col 1 reads emb(code(r,0)) through tap 0 (tap 1 is masked)
+        else if (j.col == 0) tap = 1;        // col 0: only its own (tap 1) term, col -1 is padding
+        else tap = sidx;                     // col 1: seg 0 = x_h[r,0] (tap 0), seg 1 = x_h[r,1] (tap 1)
+        return hs[l][((size_t)ch * D + ci) * 2 + tap];
+      }
+      case EPI_HRES: return hr[l][(size_t)ch * D + k];
+      case EPI_OUT1: return o1[(size_t)ch * D + k];
+      case EPI_OUT2: return o2[(size_t)ch * 512 + k];
+    }
+    return 0.f;
+  }
+  float bias(const Job& j, int jr) const {
+    int ch = chan(j, jr), l = j.layer;
+    switch (j.epi) {
+      case EPI_VERT0: case EPI_VERT: return vsb[l][ch];
+      case EPI_V2H: return v2hb[l][ch];
+      case EPI_HGATE: return hsb[l][ch];
+      case EPI_HRES: return hrb[l][ch];
+      case EPI_OUT1: return o1b[ch];
+      case EPI_OUT2: return o2b[ch];
+    }
+    return 0.f;  // FUSEV / FUSEH: bias lives in the precomputed audio term
+  }
+};
+
+static Layer pack_1x1(ts_engine* e, const float* w, int ldw, int koff, const float* b, int N, int K) {
+  std::vector<float> W((size_t)N * K), B(b, b + N);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) W[(size_t)n * K + k] = w[(size_t)n * ldw + koff + k];
+  Layer L;
+  L.N = N; L.K = K; L.taps = 1; L.cin = K;
+  L.W = e->upload(W);
+  L.bias = e->upload(B);
+  return L;
+}
+
+static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
+  const int D = PIX_D;
+  const ts_tensor* emb = ck.get("embedding.weight");
+  if (emb->ndim != 2 || emb->shape[1] != D || emb->shape[0] != PIX_NCODE)
+    fail(TS_ERR_UNSUPPORTED, "pixelcnn: only input_dim=2048, dim=256 (convert_to_6d=false) is built; got [%lld,%lld]",
+         (long long)emb->shape[0], (long long)emb->shape[1]);
+  int L = 0;
+  while (ck.has("layers." + std::to_string(L) + ".vert_stack.weight")) ++L;
+  if (L < 2 || L > 30) fail(TS_ERR_MISSING, "pixelcnn: %d layers found", L);
+  const ts_tensor* cls0 = ck.get("layers.0.class_cond_embedding.weight");
+  const int ncls = (int)cls0->shape[0];
+
+  PixelPlan* P = new PixelPlan();
+  P->L = L;
+  P->ncta = e->sm_count;
+  P->nclasses = ncls;
+  P->lay = make_layout(L);
+  if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);
+  auto stages = build_stages(L);
+  P->nstages = (int)stages.size();
+  P->table.assign((size_t)P->nstages * P->ncta, PixTask{0, 0, 0, 0, 0, 0, 0, 0});
+  WeightSrc ws(ck, L);
+  int64_t dense = 0;
+  for (int s = 0; s < P->nstages; ++s) {
+    auto& jobs = stages[s];
+    if (jobs[0].epi == EPI_SAMPLE) {
+      for (int c = 0; c < P->ncta; ++c) P->table[(size_t)s * P->ncta + c] = PixTask{EPI_SAMPLE, 0, jobs[0].col, 0, 0, 0, 0, 0};
+      continue;
+    }
+    // CTAs per job proportional to FMA cost
+    std::vector<double> cost;
+    double tot = 0;
+    for (auto& j : jobs) { double c = (double)j.nrows * std::max(j.K, 256) * j.ncol; cost.push_back(c); tot += c; }
+    std::vector<int> nc(jobs.size()), lo(jobs.size());
+    int used = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      lo[i] = (jobs[i].nrows + PIX_MAXROWS - 1) / PIX_MAXROWS;  // rows per CTA must stay <= PIX_MAXROWS
+      nc[i] = std::max(lo[i], (int)std::floor(P->ncta * cost[i] / tot));
+      used += nc[i];
+    }
+    for (size_t i = 0; used < P->ncta; i = (i + 1) % jobs.size()) { nc[i]++; used++; }
+    while (used > P->ncta) {
+      size_t big = 0; int slack = -1;
+      for (size_t i = 0; i < jobs.size(); ++i) if (nc[i] - lo[i] > slack) { slack = nc[i] - lo[i]; big = i; }
+      if (slack <= 0) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d SMs are too few for stage %d", P->ncta, s);
+      nc[big]--; used--;
+    }
+    int cta = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      const Job& j = jobs[i];
+      const int unit = j.pairs ? 2 : 1, units = j.nrows / unit;
+      const int base = units / nc[i], rem = units % nc[i];
+      int u0 = 0;
+      for (int q = 0; q < nc[i]; ++q, ++cta) {
+        int nu = base + (q < rem ? 1 : 0);
+        PixTask t{0, 0, 0, 0, 0, 0, 0, 0};
+        if (nu > 0) {
+          t.epi = j.epi; t.layer = j.layer; t.col = j.col;
+          t.row0 = u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
+          if (t.nrows > PIX_MAXROWS) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per CTA (> %d) with %d SMs", t.nrows, PIX_MAXROWS, P->ncta);
+          size_t sz = (size_t)(t.K + 1) * t.rpad;
+          if (sz > (size_t)PIX_WBUF) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: task blob %zu floats > staging buffer", sz);
+          t.wofs = (int)P->blob.size();
+          P->blob.resize(P->blob.size() + sz, 0.f);
+          float* dst = P->blob.data() + t.wofs;
+          for (int r = 0; r < t.nrows; ++r) {
+            for (int k = 0; k < t.K; ++k) dst[(size_t)k * t.rpad + r] = ws.w(j, t.row0 + r, k);
+            dst[(size_t)t.K * t.rpad + r] = ws.bias(j, t.row0 + r);
+          }
+          dense += (int64_t)t.nrows * t.K;
+        }
+        P->table[(size_t)s * P->ncta + cta] = t;
+        u0 += nu;
+      }
+    }
+  }
+  // algorithmic bytes per row: every dense PixelCNN weight + bias once — unique
+  // weights, i.e. without the duplication of the shared kw=1 vertical tap across the two output
+  // columns and without the row padding of the staged blob; mask-A-zeroed taps and the gathered
+  // tables (code embedding, class embedding) excluded.
+  {
+    int64_t w = 0;
+    for (int l = 0; l < L; ++l) {
+      w += (int64_t)2 * D * D * (l == 0 ? 3 : 2) * 3 + 2 * D;   // vert_stack (layer 0: masked row dropped)
+      w += (int64_t)2 * D * 2 * D + 2 * D;                      // vert_to_horiz
+      w += (int64_t)2 * D * D * (l == 0 ? 1 : 2) + 2 * D;       // horiz_stack (layer 0: masked tap dropped)
+      w += (int64_t)D * D + D;                                  // horiz_resid
+    }
+    w += 2 * ((int64_t)D * 2 * D + D) + ((int64_t)D * 256 + D);  // fusion_v, fusion_h, embedding_aud
+    w += (int64_t)512 * D + 512 + (int64_t)PIX_NCODE * 512 + PIX_NCODE;
+    P->row_bytes = 4 * w;
+  }
+  P->staged_row_bytes = 4 * ((int64_t)P->blob.size() + 3LL * D * D);
+  (void)dense;
+
+  // audio terms: a = embedding_aud(aud); AUDV = fusion_v[:, D:]*a + b_v; AUDH = fusion_h[:, D:]*a + b_h
+  P->emb_aud = pack_1x1(e, ck.f32("embedding_aud.weight", {D, 256, 1, 1}), 256, 0, ck.f32("embedding_aud.bias", {D}), D, 256);
+  P->fuse_v_a = pack_1x1(e, ws.fv, 2 * D, D, ck.f32("fusion_v.bias", {D}), D, D);
+  P->fuse_h_a = pack_1x1(e, ws.fh, 2 * D, D, ck.f32("fusion_h.bias", {D}), D, D);
+
+  if (!e->host_only) {
+    P->d_table = (PixTask*)e->dmalloc(P->table.size() * sizeof(PixTask));
+    TS_CUDA(cudaMemcpy(P->d_table, P->table.data(), P->table.size() * sizeof(PixTask), cudaMemcpyHostToDevice));
+    P->d_blob = e->upload(P->blob);
+    const float* ew = ck.f32("embedding.weight", {PIX_NCODE, D});
+    P->d_emb = e->upload(std::vector<float>(ew, ew + (size_t)PIX_NCODE * D));
+    std::vector<float> cls((size_t)L * ncls * 2 * D);
+    for (int l = 0; l < L; ++l) {
+      const float* c = ck.f32("layers." + std::to_string(l) + ".class_cond_embedding.weight", {ncls, 2 * D});
+      std::copy(c, c + (size_t)ncls * 2 * D, cls.begin() + (size_t)l * ncls * 2 * D);
+    }
+    P->d_cls = e->upload(cls);
+    P->d_arena = (float*)e->dmalloc((size_t)P->lay.total * sizeof(float) + 256);
+    P->d_barrier = (unsigned*)e->dmalloc(256);
+  }
+  return P;
+}
+
+// =============================================================================================
+// device
+// =============================================================================================
+struct PixArgs {
+  const PixTask* table;
+  const float* blob;
+  float* arena;
+  const float* emb;
+  const float* audv;   // [B*Ttot][256]
+  const float* audh;
+  const float* noise;  // [2T][B][2048]
+  const int64_t* pre;  // [B][T0][2] forced codes for rows < T0 (may be null when T0 == 0)
+  int64_t* idx_out;    // [B][Ttot-T0][2]
+  float* logits_out;   // [2*(Ttot-log_r0)][B][2048] or null
+  unsigned* barrier;
+  PixLayout lay;
+  int B, T0, Ttot, log_r0, L, nstages, ncta;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// CTA arrives at the grid barrier: all of this CTA's global writes become visible before the count moves
+__device__ __forceinline__ void grid_arrive(unsigned* ctr) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    red_release_add(ctr, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire(ctr) < target) { /* spin */ }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ bool task_active(const PixTask& t, int r, int log_r0) {
+  if (t.epi == EPI_IDLE) return false;
+  if (t.epi == EPI_OUT1 || t.epi == EPI_OUT2) return r >= log_r0;
+  return true;
+}
+__device__ __forceinline__ uint32_t task_bytes(const PixTask& t) { return (uint32_t)((t.K + 1) * t.rpad) * 4u; }
+
+// arena offsets (floats) of the K segments of a matmul task; returns the segment count
+__device__ __forceinline__ int resolve_segments(const PixTask& t, int pass, int r, const PixLayout& a, int L, int* seg) {
+  switch (t.epi) {
+    case EPI_VERT0:
+      for (int kh = 0; kh < 3; ++kh)
+        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.E + ((((r - 3 + kh) & 3) * 2) + ci) * PIX_SEG;
+      return 6;
+    case EPI_VERT:
+      for (int kh = 0; kh < 2; ++kh)
+        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.XV + ((t.layer * 2 + ((r - 1 + kh) & 1)) * 2 + ci) * PIX_SEG;
+      return 4;
+    case EPI_V2H:
+      seg[0] = a.HV + (((t.layer & 1) * 2 + pass) * 2) * PIX_SEG;
+      seg[1] = seg[0] + PIX_SEG;
+      return 2;
+    case EPI_FUSEV: seg[0] = a.XV1P + pass * PIX_SEG; return 1;
+    case EPI_HGATE:
+      if (t.layer == 0) {
+        if (t.col == 0) return 0;
+        seg[0] = a.E + ((r & 3) * 2 + 0) * PIX_SEG;
+        return 1;
+      }
+      seg[0] = a.XH + (0 * (L + 1) + t.layer) * PIX_SEG;
+      if (t.col == 0) return 1;
+      seg[1] = a.XH + (1 * (L + 1) + t.layer) * PIX_SEG;
+      return 2;
+    case EPI_HRES: seg[0] = a.G; return 1;
+    case EPI_FUSEH: seg[0] = a.XHP; return 1;
+    case EPI_OUT1: seg[0] = a.XH + (t.col * (L + 1) + L) * PIX_SEG; return 1;
+    case EPI_OUT2: seg[0] = a.Y; seg[1] = a.Y + PIX_SEG; return 2;
+  }
+  return 0;
+}
+
+// partial products of this CTA's rows over the warp's K slice; lane owns samples 2*lane, 2*lane+1
+template <int RC>
+__device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
+                                        float* red, int warp, int lane) {
+  float2 acc[4 * RC];
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j) acc[j] = make_float2(0.f, 0.f);
+  const int kper = K >> 3;  // K is a multiple of 256 -> 32 | kper
+  const int kbeg = warp * kper;
+  constexpr int U = 16;
+  for (int k0 = kbeg; k0 < kbeg + kper; k0 += U) {
+    const float* base = arena + seg[k0 >> 8] + ((k0 & 255) << 6) + lane * 2;
+    float2 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) x[u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4* w4 = reinterpret_cast<const float4*>(Wsm + (size_t)(k0 + u) * (4 * RC));
+#pragma unroll
+      for (int rc = 0; rc < RC; ++rc) {
+        float4 w = w4[rc];
+        acc[rc * 4 + 0].x = fmaf(w.x, x[u].x, acc[rc * 4 + 0].x); acc[rc * 4 + 0].y = fmaf(w.x, x[u].y, acc[rc * 4 + 0].y);
+        acc[rc * 4 + 1].x = fmaf(w.y, x[u].x, acc[rc * 4 + 1].x); acc[rc * 4 + 1].y = fmaf(w.y, x[u].y, acc[rc * 4 + 1].y);
+        acc[rc * 4 + 2].x = fmaf(w.z, x[u].x, acc[rc * 4 + 2].x); acc[rc * 4 + 2].y = fmaf(w.z, x[u].y, acc[rc * 4 + 2].y);
+        acc[rc * 4 + 3].x = fmaf(w.w, x[u].x, acc[rc * 4 + 3].x); acc[rc * 4 + 3].y = fmaf(w.w, x[u].y, acc[rc * 4 + 3].y);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j)
+    *reinterpret_cast<float2*>(&red[(warp * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+}
+
+__device__ __forceinline__ float red_sum(const float* red, int j, int m) {
+  float s = red[(0 * PIX_MAXROWS + j) * PIX_MB + m];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red[(w * PIX_MAXROWS + j) * PIX_MB + m];
+  return s;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// one matmul task (all passes): weights already in Wsm
+__device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, int* s_seg) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PixLayout& a = A.lay;
+  const int npass = (t.epi == EPI_V2H || t.epi == EPI_FUSEV) ? 2 : 1;
+  const float* bias = Wsm + (size_t)t.K * t.rpad;
+  float* arena = A.arena;
+  for (int pass = 0; pass < npass; ++pass) {
+    if (tid == 0) resolve_segments(t, pass, r, a, A.L, s_seg);
+    __syncthreads();  // s_seg visible; previous pass's epilogue finished reading red
+    if (t.K > 0) {
+      switch (t.rpad >> 2) {
+        case 1: mm_rows<1>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        case 2: mm_rows<2>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        case 3: mm_rows<3>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        default: mm_rows<4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+      }
+    }
+    __syncthreads();
+    const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE);
+    const int items = (pairs ? t.nrows >> 1 : t.nrows) * PIX_MB;
+    for (int it = tid; it < items; it += PIX_THREADS) {
+      const int m = it & (PIX_MB - 1), j = it >> 6;
+      if (pairs) {
+        const int q = (t.row0 >> 1) + j;  // gate channel
+        float at = (t.K > 0 ? red_sum(red, 2 * j, m) : 0.f) + bias[2 * j];
+        float as = (t.K > 0 ? red_sum(red, 2 * j + 1, m) : 0.f) + bias[2 * j + 1];
+        const float* cls = arena + a.CLS + (t.layer * 2) * PIX_SEG;
+        float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
+        if (t.epi == EPI_HGATE) {
+          const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
+          float zt = (__ldcg(v2h + q * PIX_MB + m) + at) + ct;
+          float zs = (__ldcg(v2h + (PIX_D + q) * PIX_MB + m) + as) + cs;
+          arena[a.G + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+        } else {
+          float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
+          hv[q * PIX_MB + m] = at;
+          hv[(PIX_D + q) * PIX_MB + m] = as;
+          float g = tanhf(at + ct) * sigmoidf_(as + cs);
+          if (t.epi == EPI_VERT0) arena[a.XV1P + t.col * PIX_SEG + q * PIX_MB + m] = g;
+          else if (t.layer + 1 < A.L)
+            arena[a.XV + (((t.layer + 1) * 2 + (r & 1)) * 2 + t.col) * PIX_SEG + q * PIX_MB + m] = g;
+        }
+      } else {
+        const int ch = t.row0 + j;
+        float v = red_sum(red, j, m) + bias[j];
+        switch (t.epi) {
+          case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * PIX_SEG + ch * PIX_MB + m] = v; break;
+          case EPI_FUSEV: {
+            float au = m < A.B ? A.audv[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
+            arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * PIX_SEG + ch * PIX_MB + m] = v + au;
+          } break;
+          case EPI_HRES:
+            if (t.layer == 0) arena[a.XHP + ch * PIX_MB + m] = v;
+            else {
+              float xh = __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
+              arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
+            }
+            break;
+          case EPI_FUSEH: {
+            float au = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
+            arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
+          } break;
+          case EPI_OUT1: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
+          case EPI_OUT2: arena[a.LOG + ch * PIX_MB + m] = v; break;
+        }
+      }
+    }
+  }
+}
+
+// softmax over 2048 logits + categorical draw = argmax(p / q) (ATen multinomial, num_samples = 1),
+// then embedding gather of the sampled code into the E ring.  One CTA per sample.
+__device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m, float* red) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = t.col;
+  float* sf = red;                                  // [8] scratch
+  int* si = reinterpret_cast<int*>(red + 16);       // [8] scratch
+  long long* scode = reinterpret_cast<long long*>(red + 32);
+  const bool forced = r < A.T0;
+  const bool have_logits = r >= A.log_r0;
+  float l[8];
+  if (have_logits) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = __ldcg(A.arena + A.lay.LOG + (tid + 256 * j) * PIX_MB + m);
+    if (A.logits_out) {
+      float* dst = A.logits_out + ((size_t)(2 * (r - A.log_r0) + c) * A.B + m) * PIX_NCODE;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[tid + 256 * j] = l[j];
+    }
+  }
+  long long code;
+  if (!forced) {
+    float mx = l[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) mx = fmaxf(mx, l[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sf[warp] = mx;
+    __syncthreads();
+    mx = sf[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, sf[w]);
+    __syncthreads();
+    float ex[8], sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ex[j] = expf(l[j] - mx); sum += ex[j]; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sf[warp] = sum;
+    __syncthreads();
+    sum = sf[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) sum += sf[w];
+    __syncthreads();
+    const float* q = A.noise + ((size_t)(2 * (r - A.T0) + c) * A.B + m) * PIX_NCODE;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int n = tid + 256 * j;
+      float v = (ex[j] / sum) / q[n];
+      if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sf[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (sf[w] > bv || (sf[w] == bv && si[w] < bi)) { bv = sf[w]; bi = si[w]; }
+      *scode = bi;
+    }
+    __syncthreads();
+    code = *scode;
+  } else {
+    code = A.pre[((size_t)m * A.T0 + r) * 2 + c];
+  }
+  if (r >= A.T0 && tid == 0) A.idx_out[((size_t)m * (A.Ttot - A.T0) + (r - A.T0)) * 2 + c] = code;
+  // embedding gather into the ring slot of this row (x_v = x_h = embedding(code) at layer 0)
+  A.arena[A.lay.E + ((r & 3) * 2 + c) * PIX_SEG + tid * PIX_MB + m] = A.emb[(size_t)code * PIX_D + tid];
+}
+
+constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB) * sizeof(float) + 64;
+
+template <bool PERSISTENT>
+__global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int r_single, int s_single) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wbuf = reinterpret_cast<float*>(smem_raw);
+  float* red = wbuf + 2 * PIX_WBUF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * PIX_MAXROWS * PIX_MB);
+  __shared__ int s_seg[8];
+  const int tid = threadIdx.x, cta = blockIdx.x;
+
+  if (!PERSISTENT) {
+    // debug cross-check mode: one launch per stage, weights copied synchronously
+    const PixTask t = A.table[(size_t)s_single * A.ncta + cta];
+    if (!task_active(t, r_single, A.log_r0)) return;
+    if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r_single, cta, red); return; }
+    const int nf = (t.K + 1) * t.rpad;
+    for (int i = tid; i < nf; i += PIX_THREADS) wbuf[i] = A.blob[t.wofs + i];
+    __syncthreads();
+    run_matmul_task(t, A, r_single, wbuf, red, s_seg);
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t uses[2] = {0u, 0u};
+  const int total = A.Ttot * A.nstages;
+  // prefetch the first task's weights
+  if (tid == 0) {
+    const PixTask t0 = A.table[cta];
+    if (task_active(t0, 0, A.log_r0) && t0.epi != EPI_SAMPLE) {
+      mbar_expect_tx(&bars[0], task_bytes(t0));
+      tma_load_1d(wbuf, A.blob + t0.wofs, task_bytes(t0), &bars[0]);
+    }
+  }
+  int r = 0, s = 0;
+  for (int g = 0; g < total; ++g) {
+    const PixTask t = A.table[(size_t)s * A.ncta + cta];
+    const int buf = g & 1;
+    // prefetch next stage's weight slice into the other buffer (its last reader finished before the
+    // __syncthreads of the previous grid_arrive)
+    if (tid == 0 && g + 1 < total) {
+      int s1 = s + 1, r1 = r;
+      if (s1 == A.nstages) { s1 = 0; r1 = r + 1; }
+      const PixTask tn = A.table[(size_t)s1 * A.ncta + cta];
+      if (task_active(tn, r1, A.log_r0) && tn.epi != EPI_SAMPLE) {
+        fence_proxy_async();
+        mbar_expect_tx(&bars[buf ^ 1], task_bytes(tn));
+        tma_load_1d(wbuf + (buf ^ 1) * PIX_WBUF, A.blob + tn.wofs, task_bytes(tn), &bars[buf ^ 1]);
+      }
+    }
+    const bool active = task_active(t, r, A.log_r0);
+    const bool has_w = active && t.epi != EPI_SAMPLE;  // K == 0 tasks still stage their bias row
+    if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
+    if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);  // every CTA finished stage g-1
+    if (active) {
+      if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
+      else run_matmul_task(t, A, r, wbuf + buf * PIX_WBUF, red, s_seg);
+    }
+    grid_arrive(A.barrier);
+    if (++s == A.nstages) { s = 0; ++r; }
+  }
+}
+
+__global__ void build_cls_kernel(const float* __restrict__ cls_w, const int64_t* __restrict__ label, float* arena, int cls_off,
+                                 int L, int ncls, int B) {
+  // CLS[l][ch][m] = class_cond_embedding_l[label[m]][ch]
+  int n = L * 2 * PIX_D * PIX_MB;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int m = i & (PIX_MB - 1), ch = (i >> 6) % (2 * PIX_D), l = i / (2 * PIX_D * PIX_MB);
+    float v = 0.f;
+    if (m < B) {
+      long long lb = label[m];
+      lb = lb < 0 ? 0 : (lb >= ncls ? ncls - 1 : lb);
+      v = cls_w[((size_t)l * ncls + lb) * 2 * PIX_D + ch];
+    }
+    arena[cls_off + i] = v;
+  }
+}
+
+__global__ void split_codes_kernel(const int64_t* __restrict__ idx, int64_t* __restrict__ idx_c, int64_t* codes_out, int BT) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += gridDim.x * blockDim.x) {
+    int64_t a = idx[2 * i], b = idx[2 * i + 1];
+    idx_c[i] = a;
+    idx_c[BT + i] = b;
+    if (codes_out) { codes_out[2 * i] = a; codes_out[2 * i + 1] = b; }
+  }
+}
+void split_codes(ts_engine* e, const int64_t* idx, int64_t* idx_c, int B, int T, int64_t* codes_out, cudaStream_t s) {
+  if (e->ws.sizing) return;
+  split_codes_kernel<<<cdiv(B * T, 256), 256, 0, s>>>(idx, idx_c, codes_out, B * T);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+}
+
+// logits [2T][B][2048] (step-major) -> [B][2048][T][2]
+__global__ void logits_to_ref_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T) {
+  long n = (long)2 * T * B * PIX_NCODE;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int code = i % PIX_NCODE;
+    long sb = i / PIX_NCODE;
+    int b = sb % B, step = sb / B;
+    int t = step >> 1, c = step & 1;
+    out[(((long)b * PIX_NCODE + code) * T + t) * 2 + c] = in[i];
+  }
+}
+
+static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t* label, const float* noise, int noise_B,
+                           int64_t* idx_out, float* logits_out, int B, int T, const int64_t* pre, int T0, cudaStream_t s,
+                           bool logits_all) {
+  PixelPlan* P = e->pix;
+  const int Ttot = T0 + T;
+  // audio terms for all rows of this chunk: three 256x256 GEMMs over B*Ttot rows
+  float* a_emb = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
+  float* audv = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
+  float* audh = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
+  if (e->ws.sizing) return;
+  GemmP g;
+  g.A = aud.row(b0, 0); g.W = P->emb_aud.W; g.bias = P->emb_aud.bias; g.C = a_emb;
+  g.M = B * Ttot; g.N = PIX_D; g.K = 256; g.mper = Ttot; g.a_bs = aud.bstride(); g.a_rs = aud.C; g.kc = 256; g.a_ts = 256;
+  g.c_bs = (long)Ttot * PIX_D; g.c_rs = PIX_D; g.ldw = 256;
+  launch_gemm(e, g, s);
+  GemmP h;
+  h.A = a_emb; h.W = P->fuse_v_a.W; h.bias = P->fuse_v_a.bias; h.C = audv;
+  h.M = B * Ttot; h.N = PIX_D; h.K = PIX_D; h.mper = Ttot; h.a_bs = (long)Ttot * PIX_D; h.a_rs = PIX_D; h.kc = PIX_D; h.a_ts = PIX_D;
+  h.c_bs = (long)Ttot * PIX_D; h.c_rs = PIX_D; h.ldw = PIX_D;
+  launch_gemm(e, h, s);
+  h.W = P->fuse_h_a.W; h.bias = P->fuse_h_a.bias; h.C = audh;
+  launch_gemm(e, h, s);
+
+  TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)P->lay.total * sizeof(float), s));
+  TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 256, s));
+  build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, P->lay.CLS, P->L, P->nclasses, B);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+
+  PixArgs A;
+  A.table = P->d_table; A.blob = P->d_blob; A.arena = P->d_arena; A.emb = P->d_emb;
+  A.audv = audv; A.audh = audh; A.noise = noise; A.pre = pre; A.idx_out = idx_out; A.logits_out = logits_out;
+  A.barrier = P->d_barrier; A.lay = P->lay;
+  A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
+  (void)noise_B;
+  if (e->pixel_mode == 0) {
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
+    int rs = 0, ss = 0;
+    void* args[] = {&A, &rs, &ss};
+    TS_CUDA(cudaLaunchCooperativeKernel((void*)pixelcnn_kernel<true>, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
+    e->launches++;
+  } else {
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
+    for (int r = 0; r < Ttot; ++r)
+      for (int st = 0; st < P->nstages; ++st) {
+        pixelcnn_kernel<false><<<P->ncta, PIX_THREADS, PIX_SMEM, s>>>(A, r, st);
+        e->launches++;
+      }
+    TS_CUDA(cudaGetLastError());
+  }
+}
+
+void pixelcnn_generate_act(ts_engine* e, const Act3& aud, const int64_t* label, const float* noise, int64_t* idx_out,
+                           float* logits_out, int B, int T, const int64_t* pre, int T0, cudaStream_t s, bool logits_all) {
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  if (B > PIX_MB)
+    fail(TS_ERR_UNSUPPORTED, "pixelcnn: batch tile is %d samples per call (got %d); the host shim chunks larger batches", PIX_MB, B);
+  generate_chunk(e, aud, 0, label, noise, B, idx_out, logits_out, B, T, pre, T0, s, logits_all);
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
+  TS_API_BEGIN(e)
+  Ckpt ck(tensors, n);
+  PixelPlan* P = build_plan(e, ck);
+  delete e->pix;
+  e->pix = P;
+  TS_API_END(e)
+}
+
+extern "C" int64_t ts_pixelcnn_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->row_bytes : 0; }
+
+extern "C" int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len) {
+  TS_API_BEGIN(e)
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  PixelPlan* P = e->pix;
+  const int64_t hdr = 32;
+  const int64_t tl = hdr + (int64_t)P->table.size() * 8, bl = (int64_t)P->blob.size();
+  if (table) {
+    if (*table_len < tl) fail(TS_ERR_INVALID, "table buffer too small");
+    int32_t h[32] = {P->ncta, P->nstages, P->L, PIX_D, PIX_MB, P->lay.E, P->lay.XV1P, P->lay.XV, P->lay.HV, P->lay.V2H,
+                     P->lay.G, P->lay.XHP, P->lay.XH, P->lay.Y, P->lay.LOG, P->lay.CLS, P->lay.total, PIX_NCODE};
+    memcpy(table, h, sizeof h);
+    memcpy(table + hdr, P->table.data(), P->table.size() * sizeof(PixTask));
+  }
+  if (blob) {
+    if (*blob_len < bl) fail(TS_ERR_INVALID, "blob buffer too small");
+    memcpy(blob, P->blob.data(), P->blob.size() * sizeof(float));
+  }
+  *table_len = tl;
+  *blob_len = bl;
+  TS_API_END(e)
+}
+
+static void check_pix(ts_engine* e, int B, int T) {
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  if (e->host_only) fail(TS_ERR_UNSUPPORTED, "host-only engine cannot execute");
+  if (B <= 0 || T <= 0) fail(TS_ERR_INVALID, "pixelcnn: B=%d T=%d", B, T);
+}
+
+extern "C" int ts_pixelcnn_generate(ts_engine* e, const float* aud, const int64_t* label, const float* noise,
+                                    int64_t* idx_out, float* logits_out, int B, int T, const int64_t* pre_latents, int T0,
+                                    void* stream) {
+  TS_API_BEGIN(e)
+  check_pix(e, B, T);
+  if (T0 < 0 || (T0 > 0 && !pre_latents)) fail(TS_ERR_INVALID, "pixelcnn: T0=%d without pre_latents", T0);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto body = [&] {
+    Act3 a = new_act(e, B, T0 + T, 256, 0, s);
+    nct_to_act(e, aud, 256, a, s);
+    pixelcnn_generate_act(e, a, label, noise, idx_out, logits_out, B, T, pre_latents, T0, s);
+  };
+  e->ws.begin_sizing(); body();
+  size_t need = e->ws.need;
+  e->ws.buf.ensure(need + 256);
+  e->ws.begin(need); body();
+  TS_API_END(e)
+}
+
+extern "C" int ts_pixelcnn_logits(ts_engine* e, const float* aud, const int64_t* label, const int64_t* codes,
+                                  float* logits_out, int B, int T, void* stream) {
+  TS_API_BEGIN(e)
+  check_pix(e, B, T);
+  cudaStream_t s = (cudaStream_t)stream;
+  auto body = [&] {
+    Act3 a = new_act(e, B, T, 256, 0, s);
+    nct_to_act(e, aud, 256, a, s);
+    float* steps = e->ws.alloc<float>((size_t)2 * T * B * PIX_NCODE);
+    int64_t* dummy = e->ws.alloc<int64_t>(16);
+    // all rows forced (T0 = T, nothing sampled), logits recorded for every row
+    pixelcnn_generate_act(e, a, label, nullptr, dummy, steps, B, 0, codes, T, s, true);
+    if (!e->ws.sizing) {
+      long n = (long)2 * T * B * PIX_NCODE;
+      logits_to_ref_kernel<<<(int)std::min<long>((n + 255) / 256, 148 * 16), 256, 0, s>>>(steps, logits_out, B, T);
+      e->launches++;
+      TS_CUDA(cudaGetLastError());
+    }
+  };
+  e->ws.begin_sizing(); body();
+  size_t need = e->ws.need;
+  e->ws.buf.ensure(need + 256);
+  e->ws.begin(need); body();
+  TS_API_END(e)
+}

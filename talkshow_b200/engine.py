@@ -1,0 +1,213 @@
+"""Thin object wrapper over the C ABI: PyTorch CUDA tensors in, PyTorch CUDA tensors out.
+
+Module-level mirror of the reference network modules (nets/spg/*.py) — used by the wrapper classes
+in talkshow_b200/nets/ and directly by the parity tests.  Every method enqueues on the current
+CUDA stream of the engine's device and returns without synchronising.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+PIX_TILE = 64  # samples per PixelCNN launch (csrc/pixelcnn.h PIX_MB)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        dev = device if isinstance(device, int) else torch.device(device).index or 0
+        rc = self.L.ts_engine_create(C.byref(h), dev)
+        if rc:
+            raise RuntimeError("ts_engine_create(%d): %s" % (dev, self.L.ts_last_error(None).decode()))
+        self.h = h
+        self.host_only = dev < 0
+        self.device = torch.device("cuda", dev) if dev >= 0 else torch.device("cpu")
+        self.loaded = set()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ts_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError("%s failed (status %d): %s" % (what, rc, self.L.ts_last_error(self.h).decode()))
+
+    def _s(self):
+        return _lib.stream_ptr(self.device)
+
+    def _dev(self, t, dtype):
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    @property
+    def sm_count(self):
+        return self.L.ts_engine_sm_count(self.h)
+
+    @property
+    def launches(self):
+        return int(self.L.ts_launch_count(self.h))
+
+    @property
+    def pixelcnn_row_bytes(self):
+        return int(self.L.ts_pixelcnn_row_bytes(self.h))
+
+    def set_pixelcnn_mode(self, mode):
+        self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
+
+    # -- weights ---------------------------------------------------------------------------------
+    def load_pixelcnn(self, sd):
+        arr, keep = _lib.pack_tensors(sd)
+        self._check(self.L.ts_load_pixelcnn(self.h, arr, len(sd)), "ts_load_pixelcnn")
+        self.loaded.add("pixelcnn")
+
+    def load_audioenc(self, sd):
+        arr, keep = _lib.pack_tensors(sd)
+        self._check(self.L.ts_load_audioenc(self.h, arr, len(sd)), "ts_load_audioenc")
+        self.loaded.add("audioenc")
+
+    def load_vq(self, which, sd):
+        arr, keep = _lib.pack_tensors(sd)
+        self._check(self.L.ts_load_vq(self.h, which, arr, len(sd)), "ts_load_vq")
+        self.loaded.add("vq%d" % which)
+
+    def load_face(self, sd):
+        sd = dict(sd)
+        p = "audio_encoder.encoder.pos_conv_embed.conv."
+        if p + "weight" not in sd:      # resolve the weight_norm parametrisation (dim=2), old or new names
+            if p + "parametrizations.weight.original0" in sd:
+                g, v = sd.pop(p + "parametrizations.weight.original0"), sd.pop(p + "parametrizations.weight.original1")
+            else:
+                g, v = sd.pop(p + "weight_g"), sd.pop(p + "weight_v")
+            sd[p + "weight"] = torch._weight_norm(v.float().cpu(), g.float().cpu(), 2)
+        arr, keep = _lib.pack_tensors(sd)
+        self._check(self.L.ts_load_face(self.h, arr, len(sd)), "ts_load_face")
+        self.loaded.add("face")
+
+    # -- modules ---------------------------------------------------------------------------------
+    def latent_rows(self, M):
+        return self.L.ts_latent_rows(M)
+
+    def audio_encode(self, mfcc):
+        """AudioEncoder.forward: [B,64,M] -> [B,256,T]."""
+        mfcc = self._dev(mfcc, torch.float32)
+        B, _, M = mfcc.shape
+        out = torch.empty(B, 256, self.latent_rows(M), device=self.device)
+        self._check(self.L.ts_audio_encode(self.h, _lib.ptr(mfcc), _lib.ptr(out), B, M, self._s()), "ts_audio_encode")
+        return out
+
+    def pixelcnn_generate(self, aud, label, noise, T=None, pre_latents=None, want_logits=False):
+        """GatedPixelCNN.generate: aud [B,256,T0+T], label [B], noise [2T,B,2048] -> codes [B,T,2]
+        (+ logits [2T,B,2048]).  Batches above the 64-sample tile are chunked here."""
+        aud = self._dev(aud, torch.float32)
+        label = self._dev(label, torch.int64)
+        noise = self._dev(noise, torch.float32)
+        B = aud.shape[0]
+        T0 = 0 if pre_latents is None else pre_latents.shape[1]
+        T = aud.shape[2] - T0 if T is None else T
+        if label.numel() == 1 and B > 1:
+            label = label.expand(B).contiguous()
+        pre = None if pre_latents is None else self._dev(pre_latents, torch.int64)
+        codes = torch.empty(B, T, 2, dtype=torch.int64, device=self.device)
+        logits = torch.empty(2 * T, B, 2048, device=self.device) if want_logits else None
+        for b0 in range(0, B, PIX_TILE):
+            b1 = min(B, b0 + PIX_TILE)
+            nb = b1 - b0
+            full = nb == B
+            nz = noise if full else noise[:, b0:b1].contiguous()
+            cz = codes if full else torch.empty(nb, T, 2, dtype=torch.int64, device=self.device)
+            lz = logits if (full or logits is None) else torch.empty(2 * T, nb, 2048, device=self.device)
+            self._check(self.L.ts_pixelcnn_generate(
+                self.h, _lib.ptr(aud[b0:b1].contiguous()), _lib.ptr(label[b0:b1].contiguous()), _lib.ptr(nz),
+                _lib.ptr(cz), _lib.ptr(lz), nb, T, _lib.ptr(None if pre is None else pre[b0:b1].contiguous()), T0,
+                self._s()), "ts_pixelcnn_generate")
+            if not full:
+                codes[b0:b1] = cz
+                if logits is not None:
+                    logits[:, b0:b1] = lz
+        return (codes, logits) if want_logits else codes
+
+    def pixelcnn_logits(self, aud, label, codes):
+        """GatedPixelCNN.forward (teacher forced): -> logits [B,2048,T,2]."""
+        aud = self._dev(aud, torch.float32)
+        label = self._dev(label, torch.int64)
+        codes = self._dev(codes, torch.int64)
+        B, _, T = aud.shape
+        assert B <= PIX_TILE
+        out = torch.empty(B, 2048, T, 2, device=self.device)
+        self._check(self.L.ts_pixelcnn_logits(self.h, _lib.ptr(aud), _lib.ptr(label), _lib.ptr(codes), _lib.ptr(out),
+                                              B, T, self._s()), "ts_pixelcnn_logits")
+        return out
+
+    def vq_decode(self, which, idx):
+        """VQVAE.decode(latents=idx): [B,T] -> [B,C,4T]."""
+        idx = self._dev(idx, torch.int64)
+        B, T = idx.shape
+        C_ = 39 if which == 0 else 90
+        out = torch.empty(B, C_, 4 * T, device=self.device)
+        self._check(self.L.ts_vq_decode(self.h, which, _lib.ptr(idx), _lib.ptr(out), B, T, self._s()), "ts_vq_decode")
+        return out
+
+    def vq_encode(self, which, poses, want_e=False):
+        """VQVAE.encode: poses [B,F,C] -> idx [B,T] (and e [B,64,T])."""
+        poses = self._dev(poses, torch.float32)
+        B, F, _ = poses.shape
+        T = self.latent_rows(F)
+        idx = torch.empty(B, T, dtype=torch.int64, device=self.device)
+        e = torch.empty(B, 64, T, device=self.device) if want_e else None
+        self._check(self.L.ts_vq_encode(self.h, which, _lib.ptr(poses), _lib.ptr(idx), _lib.ptr(e), B, F, self._s()),
+                    "ts_vq_encode")
+        return (idx, e) if want_e else idx
+
+    def face_forward(self, wave, id_onehot, frame):
+        """s2g_face.Generator.forward: wave [B,N], id [B,4] -> [B,frame,103]."""
+        wave = self._dev(wave, torch.float32)
+        B, N = wave.shape
+        idv = self._dev(id_onehot, torch.float32)
+        if idv.shape[0] == 1 and B > 1:
+            idv = idv.expand(B, -1).contiguous()
+        out = torch.empty(B, frame, 103, device=self.device)
+        self._check(self.L.ts_face_forward(self.h, _lib.ptr(wave), _lib.ptr(idv), _lib.ptr(out), B, N, frame,
+                                           self._s()), "ts_face_forward")
+        return out
+
+    def body_generate(self, mfcc, label, noise, want_codes=True):
+        """fused s2g_body_pixel core: mfcc [B,64,M] -> (codes [B,T,2], poses [B,4T,129])."""
+        mfcc = self._dev(mfcc, torch.float32)
+        label = self._dev(label, torch.int64)
+        noise = self._dev(noise, torch.float32)
+        B, _, M = mfcc.shape
+        if label.numel() == 1 and B > 1:
+            label = label.expand(B).contiguous()
+        T = self.latent_rows(M)
+        codes = torch.empty(B, T, 2, dtype=torch.int64, device=self.device) if want_codes else None
+        poses = torch.empty(B, 4 * T, 129, device=self.device)
+        for b0 in range(0, B, PIX_TILE):
+            b1 = min(B, b0 + PIX_TILE)
+            full = (b1 - b0) == B
+            nz = noise if full else noise[:, b0:b1].contiguous()
+            self._check(self.L.ts_body_generate(
+                self.h, _lib.ptr(mfcc[b0:b1]), _lib.ptr(label[b0:b1]), _lib.ptr(nz),
+                _lib.ptr(None if codes is None else codes[b0:b1]), _lib.ptr(poses[b0:b1]), b1 - b0, M, self._s()),
+                "ts_body_generate")
+        return codes, poses
+
+    def assemble_pose(self, face, body, stand=False):
+        """demo.py:182-229 + part2full: face [B,Ff,103], body [B,Fb,129] -> [B,Ff,265]."""
+        face = self._dev(face, torch.float32)
+        body = self._dev(body, torch.float32)
+        B, Ff, _ = face.shape
+        out = torch.empty(B, Ff, 265, device=self.device)
+        self._check(self.L.ts_assemble_pose(self.h, _lib.ptr(face), _lib.ptr(body), _lib.ptr(out), B, Ff,
+                                            body.shape[1], int(stand), self._s()), "ts_assemble_pose")
+        return out

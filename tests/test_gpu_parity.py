@@ -1,0 +1,185 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI, against the CPU oracle on the same
+seeded inputs and against the reference-generated golden fixtures.
+
+Bars (BASELINE.json north_star): bit-exact VQ code indices (sampled sequences and argmin
+encodes); floating-point outputs within 1e-4 max-abs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import talkshow_oracle as O
+from conftest import GOLDEN, draw_noise, noise_fp
+from talkshow_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.fixture(scope="module")
+def eng(ckpts):
+    from talkshow_b200.engine import Engine
+
+    e = Engine(0)
+    e.load_pixelcnn(ckpts["pixel"]["generator"])
+    e.load_audioenc(ckpts["pixel"]["audioencoder"])
+    e.load_vq(0, ckpts["vq"]["g_body"])
+    e.load_vq(1, ckpts["vq"]["g_hand"])
+    yield e
+    torch.cuda.synchronize()
+    e.close()
+
+
+def test_audio_encoder(eng, ckpts):
+    for B, M in ((1, 120), (3, 300), (2, 37)):
+        mfcc = synth.synth_mfcc(B, M, seed=21)
+        ref = O.audio_encoder(ckpts["pixel"]["audioencoder"], mfcc)
+        got = eng.audio_encode(mfcc).cpu()
+        assert got.shape == ref.shape
+        assert (got - ref).abs().max().item() <= TOL
+
+
+def test_vq_decode(eng, ckpts):
+    g = torch.Generator().manual_seed(7)
+    for which, key in ((0, "g_body"), (1, "g_hand")):
+        for B, T in ((1, 22), (3, 75), (2, 1)):
+            idx = torch.randint(0, 2048, (B, T), generator=g)
+            ref = O.vq_decode(ckpts["vq"][key], idx)
+            got = eng.vq_decode(which, idx).cpu()
+            assert got.shape == ref.shape
+            assert (got - ref).abs().max().item() <= TOL
+
+
+def test_vq_encode_indices(eng, ckpts):
+    gold = _load("vq_roundtrip")
+    poses = synth.synth_poses(2, 88)
+    gt = poses[:, O.C_INDEX_3D].permute(0, 2, 1).contiguous()
+    ib, eb = eng.vq_encode(0, gt[..., :39].contiguous(), want_e=True)
+    ih = eng.vq_encode(1, gt[..., 39:].contiguous())
+    assert np.array_equal(ib.cpu().numpy(), gold["idx_body"])       # reference-generated golden
+    assert np.array_equal(ih.cpu().numpy(), gold["idx_hand"])
+    assert np.abs(eb.cpu().numpy() - gold["e_body"]).max() == 0.0    # gathered codebook rows: exact
+    # larger seeded case against the oracle
+    poses = synth.synth_poses(4, 240, seed=9)
+    gt = poses[:, O.C_INDEX_3D].permute(0, 2, 1).contiguous()
+    for which, key, sl in ((0, "g_body", slice(0, 39)), (1, "g_hand", slice(39, 129))):
+        _, ref = O.vq_encode(ckpts["vq"][key], gt[..., sl])
+        got = eng.vq_encode(which, gt[..., sl].contiguous()).cpu()
+        assert torch.equal(got, ref)
+
+
+def test_vq_roundtrip_output(eng, ckpts):
+    gold = _load("vq_roundtrip")
+    poses = synth.synth_poses(2, 88)
+    gt = poses[:, O.C_INDEX_3D].permute(0, 2, 1).contiguous()
+    ib = eng.vq_encode(0, gt[..., :39].contiguous())
+    ih = eng.vq_encode(1, gt[..., 39:].contiguous())
+    pred = torch.cat([eng.vq_decode(0, ib), eng.vq_decode(1, ih)], 1).transpose(1, 2).cpu()   # [B,F,129]
+    out = torch.cat(list(pred), 1).numpy()                                                   # (F, B*129)
+    assert np.abs(out - gold["out"]).max() <= TOL
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_pixelcnn_teacher_forced_logits(eng, ckpts, mode):
+    """mode 1 = one launch per stage (cross-check), mode 0 = persistent cooperative kernel."""
+    eng.set_pixelcnn_mode(mode)
+    try:
+        sd = ckpts["pixel"]["generator"]
+        B, T = 3, 6
+        g = torch.Generator().manual_seed(3)
+        codes = torch.randint(0, 2048, (B, T, 2), generator=g)
+        label = torch.tensor([0, 3, 1])
+        aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], synth.synth_mfcc(B, 4 * T, seed=5))
+        ref = O.pixelcnn_forward(sd, codes, label, aud.unsqueeze(-1).repeat(1, 1, 1, 2))
+        got = eng.pixelcnn_logits(aud, label, codes).cpu()
+        err = (got - ref).abs().max().item()
+        print("teacher-forced logits max-abs err (mode %d): %.3e (logit std %.2f)" % (mode, err, ref.std().item()))
+        assert err <= TOL
+    finally:
+        eng.set_pixelcnn_mode(0)
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_pixelcnn_generate_b1_t30(eng, ckpts, mode):
+    """BASELINE config 3: B=1, 4 s, id=0 — bit-exact code sequence vs oracle and golden."""
+    eng.set_pixelcnn_mode(mode)
+    try:
+        gold = _load("pixel_b1_t30")
+        mfcc = synth.synth_mfcc(1, 120)
+        noise = draw_noise(60, 1, int(gold["sampler_seed"]))
+        aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], mfcc)
+        ref, ref_logits = O.pixelcnn_generate(ckpts["pixel"]["generator"], torch.tensor([0]), 30, 1,
+                                              aud.unsqueeze(-1).repeat(1, 1, 1, 2), noise=noise, window=18,
+                                              return_logits=True)
+        got, logits = eng.pixelcnn_generate(aud, torch.tensor([0]), noise, want_logits=True)
+        got = got.cpu()
+        first_bad = (got != ref).flatten().nonzero()
+        assert torch.equal(got, ref), "first mismatch at flat index %s" % first_bad[:1].tolist()
+        assert (logits.cpu() - ref_logits).abs().max().item() <= TOL
+        if np.allclose(gold["noise_fp"], noise_fp(noise), rtol=0, atol=1e-9):
+            assert np.array_equal(got.numpy(), gold["codes"])
+    finally:
+        eng.set_pixelcnn_mode(0)
+
+
+def test_pixelcnn_generate_b3_t75(eng, ckpts):
+    gold = _load("pixel_b3_t75")
+    mfcc = synth.synth_mfcc(3, 300, seed=int(gold["mfcc_seed"]))
+    noise = draw_noise(150, 3, int(gold["sampler_seed"]))
+    label = torch.tensor(gold["label"])
+    ref, _ = O.body_generate(ckpts["pixel"], ckpts["vq"], mfcc, label, noise=noise, window=18)
+    codes, poses = eng.body_generate(mfcc, label, noise)
+    assert torch.equal(codes.cpu(), ref)
+    if np.allclose(gold["noise_fp"], noise_fp(noise), rtol=0, atol=1e-9):
+        assert np.array_equal(codes.cpu().numpy(), gold["codes"])
+        assert np.abs(poses.cpu().numpy()[:, ::int(gold["pred_stride"])] - gold["pred"]).max() <= TOL
+
+
+def test_pixelcnn_continuity(eng, ckpts):
+    """generate(pre_latents, pre_audio), gated_pixelcnn_v2.py:158-165."""
+    gold = _load("pixel_cont")
+    mfcc = synth.synth_mfcc(2, 160, seed=int(gold["mfcc_seed"]))
+    noise = draw_noise(80, 2, int(gold["sampler_seed"]))
+    label = torch.tensor(gold["label"])
+    aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], mfcc)
+    a2 = aud.unsqueeze(-1).repeat(1, 1, 1, 2)
+    sd = ckpts["pixel"]["generator"]
+    ref0 = O.pixelcnn_generate(sd, label, 15, 2, a2[:, :, :15], noise=noise[:30], window=18)
+    ref1 = O.pixelcnn_generate(sd, label, 25, 2, a2[:, :, 15:], noise=noise[30:], pre_latents=ref0,
+                               pre_audio=a2[:, :, :15], window=18)
+    got0 = eng.pixelcnn_generate(aud[:, :, :15], label, noise[:30])
+    got1 = eng.pixelcnn_generate(aud, label, noise[30:], T=25, pre_latents=got0)
+    assert torch.equal(got0.cpu(), ref0)
+    assert torch.equal(got1.cpu(), ref1)
+
+
+def test_body_generate_fused_b12(eng, ckpts):
+    """config-4-like: 12 diversity samples of one clip, one speaker (T kept small for the CPU oracle)."""
+    B, M = 12, 80
+    mfcc = synth.synth_mfcc(1, M, seed=31).repeat(B, 1, 1)
+    label = torch.zeros(B, dtype=torch.int64)
+    T = O.latent_rows(M)
+    noise = draw_noise(2 * T, B, 99)
+    ref_codes, ref_poses = O.body_generate(ckpts["pixel"], ckpts["vq"], mfcc, label, noise=noise, window=18)
+    codes, poses = eng.body_generate(mfcc, label, noise)
+    assert torch.equal(codes.cpu(), ref_codes)
+    assert (poses.cpu() - ref_poses).abs().max().item() <= TOL
+    # diversity: different noise rows give different sequences
+    assert len({tuple(c.flatten().tolist()) for c in codes.cpu()}) > 1
+
+
+def test_assemble_pose(eng):
+    g = torch.Generator().manual_seed(1)
+    face = torch.rand(2, 9, 103, generator=g)
+    body = torch.rand(2, 7, 129, generator=g)
+    got = eng.assemble_pose(face, body).cpu()
+    for b in range(2):
+        assert torch.equal(got[b], O.assemble_pose(face[b], body[b]))
+    got = eng.assemble_pose(face, body, stand=True).cpu()
+    assert torch.equal(got[1], O.assemble_pose(face[1], body[1], stand=True))

@@ -1,0 +1,84 @@
+"""CPU: the PixelCNN execution plan (stage table + packed weights built by the C++ packer in
+host-only mode) reproduces the oracle's logits and sampled codes when interpreted in numpy."""
+import numpy as np
+import pytest
+import torch
+
+import plan_emulator as PE
+import talkshow_oracle as O
+from conftest import draw_noise
+from talkshow_b200 import _lib, synth
+from talkshow_b200.engine import Engine
+
+
+@pytest.fixture(scope="module")
+def plan(ckpts):
+    e = Engine(-148)            # host-only planning engine sized for 148 SMs
+    e.load_pixelcnn(ckpts["pixel"]["generator"])
+    table, blob = _lib.plan_to_numpy(e.h)
+    rb = e.pixelcnn_row_bytes
+    e.close()
+    return PE.Plan(table, blob), rb
+
+
+def _audio_terms(sd, aud):
+    """aud [B,256,T] -> AUDV, AUDH [B,T,256] (what the engine precomputes with three GEMMs)."""
+    a = torch.einsum("oc,bct->bto", sd["embedding_aud.weight"][:, :, 0, 0], aud) + sd["embedding_aud.bias"]
+    av = torch.einsum("oc,btc->bto", sd["fusion_v.weight"][:, 256:, 0, 0], a) + sd["fusion_v.bias"]
+    ah = torch.einsum("oc,btc->bto", sd["fusion_h.weight"][:, 256:, 0, 0], a) + sd["fusion_h.bias"]
+    return av.numpy(), ah.numpy()
+
+
+def test_plan_shape(plan):
+    p, row_bytes = plan
+    assert p.ncta == 148 and p.L == 15 and p.nstages == 84
+    assert row_bytes == 89774080        # SURVEY.md §8d algorithmic bytes per latent row
+    t = p.table
+    assert (t[:, :, 4] <= 16).all()
+    # every output row of every stage is owned by exactly one CTA
+    for s in range(p.nstages):
+        for epi, layer, col in {tuple(x) for x in t[s][:, :3].tolist() if x[0] not in (0, 10)}:
+            sel = t[s][(t[s][:, 0] == epi) & (t[s][:, 1] == layer) & (t[s][:, 2] == col)]
+            rows = sorted((int(r0), int(n)) for r0, n in sel[:, 3:5])
+            pos = 0
+            for r0, n in rows:
+                assert r0 == pos
+                pos += n
+            assert pos in (256, 512, 2048)
+
+
+def test_plan_teacher_forced_logits(plan, ckpts):
+    p, _ = plan
+    sd = ckpts["pixel"]["generator"]
+    B, T = 3, 6
+    g = torch.Generator().manual_seed(3)
+    codes = torch.randint(0, 2048, (B, T, 2), generator=g)
+    label = torch.tensor([0, 3, 1])
+    aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], synth.synth_mfcc(B, 4 * T, seed=5))
+    ref = O.pixelcnn_forward(sd, codes, label, aud.unsqueeze(-1).repeat(1, 1, 1, 2))     # [B,2048,T,2]
+    av, ah = _audio_terms(sd, aud)
+    cls_w = [sd["layers.%d.class_cond_embedding.weight" % l].numpy() for l in range(p.L)]
+    got_codes, logits = PE.run(p, sd["embedding.weight"].numpy(), cls_w, av, ah, label.numpy(), codes.numpy(), T)
+    assert np.array_equal(got_codes, codes.numpy())
+    got = np.transpose(logits, (2, 3, 0, 1))                                             # [B,2048,T,2]
+    err = np.abs(got - ref.numpy()).max()
+    assert err <= 2e-4, err
+
+
+def test_plan_sampling_with_prefix(plan, ckpts):
+    """free-running sampling after a forced prefix == oracle generate(pre_latents=...)."""
+    p, _ = plan
+    sd = ckpts["pixel"]["generator"]
+    B, T0, T = 2, 2, 3
+    label = torch.tensor([2, 0])
+    aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], synth.synth_mfcc(B, 4 * (T0 + T), seed=6))
+    a2 = aud.unsqueeze(-1).repeat(1, 1, 1, 2)
+    g = torch.Generator().manual_seed(4)
+    pre = torch.randint(0, 2048, (B, T0, 2), generator=g)
+    noise = draw_noise(2 * T, B, 11)
+    ref = O.pixelcnn_generate(sd, label, T, B, a2[:, :, T0:], noise=noise, pre_latents=pre, pre_audio=a2[:, :, :T0])
+    av, ah = _audio_terms(sd, aud)
+    cls_w = [sd["layers.%d.class_cond_embedding.weight" % l].numpy() for l in range(p.L)]
+    got, _ = PE.run(p, sd["embedding.weight"].numpy(), cls_w, av, ah, label.numpy(), pre.numpy(), T0 + T,
+                    noise=noise.numpy(), T0=T0)
+    assert np.array_equal(got[:, T0:], ref.numpy())
