@@ -111,6 +111,12 @@ int64_t ts_launch_count(ts_engine* e);
 /* device time of the last ts_pixelcnn_generate persistent-kernel launch is measured by the caller
  * with events; this returns the algorithmic weight bytes one latent row touches. */
 int64_t ts_pixelcnn_row_bytes(ts_engine* e);
+/* bytes the kernel actually stages per row (packed blob incl. row padding / per-column duplication) */
+int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e);
+/* enable CUDA-event timing around the persistent kernel (events on its launch stream) and read the
+ * duration of the most recent launch in ms (synchronises on the end event; -1 if none). */
+int ts_pixelcnn_timing(ts_engine* e, int enable);
+double ts_pixelcnn_last_ms(ts_engine* e);
 /* Export the PixelCNN execution plan (stage table + packed weight blob) to host buffers so a test
  * can interpret it on the CPU; sizes are returned when the buffers are NULL. */
 int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len);

@@ -47,6 +47,9 @@ SYMBOLS = {
                                    C.c_int, C.c_void_p]),
     "ts_launch_count": (C.c_int64, [C.c_void_p]),
     "ts_pixelcnn_row_bytes": (C.c_int64, [C.c_void_p]),
+    "ts_pixelcnn_staged_row_bytes": (C.c_int64, [C.c_void_p]),
+    "ts_pixelcnn_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "ts_pixelcnn_last_ms": (C.c_double, [C.c_void_p]),
     "ts_debug_pixelcnn_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p,
                                          C.POINTER(C.c_int64)]),
     "ts_set_pixelcnn_mode": (C.c_int, [C.c_void_p, C.c_int]),

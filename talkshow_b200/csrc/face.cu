@@ -1,16 +1,526 @@
-// talkshow_b200 — face regressor (s2g_face.Generator): placeholder translation unit until the
-// wav2vec2 path lands; ts_load_face / ts_face_forward report TS_ERR_UNSUPPORTED.
+// talkshow_b200 — face regressor: s2g_face.Generator.forward (nets/spg/s2g_face.py:196-224) with the
+// reference's wav2vec2 variant (nets/spg/wav2vec.py:76-143: HF Wav2Vec2Model whose CNN features are
+// linearly interpolated from 50 to 30 fps before the transformer).  Everything runs channel-last
+// ([B,T,C]) so that every Conv1d / Linear is one implicit GEMM (kernels.h); GroupNorm(512,512),
+// LayerNorm, the 50->30 fps interpolation and the 12-head attention are small dedicated kernels.
+// fp32 throughout (the parity bar is 1e-4 max-abs on the 103 outputs).
+#include "convstack.h"
 #include "pixelcnn.h"
+
 namespace ts {
-void face_destroy(ts_engine*) {}
+
+static const int W2V_K[7] = {10, 3, 3, 3, 3, 2, 2};
+static const int W2V_S[7] = {5, 2, 2, 2, 2, 2, 2};
+
+struct EncLayer {
+  Layer qkv, out, ff1, ff2;
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+
+struct FaceNet {
+  float* conv0_w = nullptr;  // [512][10]
+  float *gn_g = nullptr, *gn_b = nullptr;
+  Layer conv[7];  // 1..6 used
+  float *fp_ln_g = nullptr, *fp_ln_b = nullptr;
+  Layer fproj, posconv;
+  float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
+  std::vector<EncLayer> layers;
+  Layer feat_map;
+  float *id_w = nullptr, *id_b = nullptr;  // [64][ncls], [64]
+  int ncls = 4;
+  Layer fn_conv[3], fn_res0;
+  float *fn_g[3], *fn_b[3];
+  Layer dec_conv[2][3];
+  float *dec_g[2][3], *dec_b[2][3];
+  Layer fin[2];
+  int jaw_dim = 3, exp_dim = 100;
+};
+
+void face_destroy(ts_engine* e) {
+  delete e->face;
+  e->face = nullptr;
 }
-extern "C" int ts_load_face(ts_engine* e, const ts_tensor*, int) {
-  if (!e) return TS_ERR_INVALID;
-  e->err = "face path not built yet";
-  return TS_ERR_UNSUPPORTED;
+
+static float* up(ts_engine* e, const float* p, size_t n) { return e->upload(std::vector<float>(p, p + n)); }
+
+// weight [cout][cin][k] -> Layer [cout][k][cin] (+ optional bias)
+static Layer pack_ckc(ts_engine* e, const float* w, const float* b, int cout, int cin, int k) {
+  int cp = pad4(cin);
+  std::vector<float> W((size_t)cout * k * cp, 0.f);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < k; ++t) W[((size_t)o * k + t) * cp + c] = w[((size_t)o * cin + c) * k + t];
+  Layer L;
+  L.N = cout; L.taps = k; L.cin = cp; L.K = k * cp;
+  L.W = e->upload(W);
+  L.bias = b ? up(e, b, cout) : nullptr;
+  return L;
 }
-extern "C" int ts_face_forward(ts_engine* e, const float*, const float*, float*, int, int, int, void*) {
-  if (!e) return TS_ERR_INVALID;
-  e->err = "face path not built yet";
-  return TS_ERR_UNSUPPORTED;
+static Layer pack_linear(ts_engine* e, const float* w, const float* b, int N, int K) {
+  Layer L;
+  L.N = N; L.K = K; L.taps = 1; L.cin = K;
+  L.W = up(e, w, (size_t)N * K);
+  L.bias = b ? up(e, b, N) : nullptr;
+  return L;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------
+// conv0 (1 -> 512 channels, k=10, s=5, no bias) statistics for GroupNorm(512 groups): per (b, c)
+// sum and sum of squares over time, accumulated in fp64.
+__global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restrict__ wave, const float* __restrict__ w, int N, int T0,
+                                                          double* __restrict__ stats) {
+  constexpr int TC = 256;  // outputs per block
+  __shared__ float xs[TC * 5 + 16];
+  const int b = blockIdx.y, t0 = blockIdx.x * TC, tid = threadIdx.x;
+  const int nt = min(TC, T0 - t0);
+  const float* x = wave + (size_t)b * N + (size_t)t0 * 5;
+  for (int i = tid; i < nt * 5 + 5; i += 256) xs[i] = x[i];
+  __syncthreads();
+  for (int c = tid; c < 512; c += 256) {
+    float wr[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) wr[j] = w[c * 10 + j];
+    double s = 0.0, ss = 0.0;
+    for (int t = 0; t < nt; ++t) {
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) y = fmaf(wr[j], xs[t * 5 + j], y);
+      s += (double)y;
+      ss += (double)y * (double)y;
+    }
+    atomicAdd(&stats[((size_t)b * 512 + c) * 2], s);
+    atomicAdd(&stats[((size_t)b * 512 + c) * 2 + 1], ss);
+  }
+}
+// recompute conv0, normalise per (b,c), affine, GELU, write channel-last [B,T0,512]
+__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wave, const float* __restrict__ w,
+                                                          const double* __restrict__ stats, const float* __restrict__ g,
+                                                          const float* __restrict__ bta, int N, int T0, float* __restrict__ out) {
+  constexpr int TC = 64;
+  __shared__ float xs[TC * 5 + 16];
+  const int b = blockIdx.y, t0 = blockIdx.x * TC, tid = threadIdx.x;
+  const int nt = min(TC, T0 - t0);
+  const float* x = wave + (size_t)b * N + (size_t)t0 * 5;
+  for (int i = tid; i < nt * 5 + 5; i += 256) xs[i] = x[i];
+  __syncthreads();
+  for (int c = tid; c < 512; c += 256) {
+    float wr[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) wr[j] = w[c * 10 + j];
+    double s = stats[((size_t)b * 512 + c) * 2], ss = stats[((size_t)b * 512 + c) * 2 + 1];
+    double mean = s / T0, var = ss / T0 - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + 1e-5)), mu = (float)mean, gg = g[c], bb = bta[c];
+    for (int t = 0; t < nt; ++t) {
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) y = fmaf(wr[j], xs[t * 5 + j], y);
+      float v = (y - mu) * rstd * gg + bb;
+      v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+      out[((size_t)b * T0 + t0 + t) * 512 + c] = v;
+    }
+  }
+}
+
+// F.interpolate(mode='linear', align_corners=False) along time, channel-last
+__global__ void interp_kernel(Act3 in, Act3 out) {
+  const float scale = (float)in.T / (float)out.T;
+  long n = (long)out.B * out.T * out.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = i % out.C;
+    long bt = i / out.C;
+    int t = bt % out.T, b = bt / out.T;
+    float src = scale * (t + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    int i0 = (int)src;
+    if (i0 > in.T - 1) i0 = in.T - 1;
+    int i1 = i0 + (i0 < in.T - 1 ? 1 : 0);
+    float l1 = src - (float)i0, l0 = 1.0f - l1;
+    out.row(b, t)[c] = l0 * in.row(b, i0)[c] + l1 * in.row(b, i1)[c];
+  }
+}
+
+// y = LayerNorm_C(x + pre) * g + b  (+ res) -> act ; one warp per row
+__global__ void ln_pre_kernel(Act3 x, Act3 pre, int has_pre, const float* __restrict__ g, const float* __restrict__ bta, Act3 y,
+                              Act3 res, int has_res, int act, float eps) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int rows = x.B * x.T;
+  if (warp >= rows) return;
+  int b = warp / x.T, t = warp % x.T, C = x.C;
+  const float* xr = x.row(b, t);
+  const float* pr = has_pre ? pre.row(b, t) : nullptr;
+  float v[24];  // C <= 768
+  float s = 0.f;
+  int n = 0;
+  for (int c = lane; c < C; c += 32, ++n) {
+    float a = xr[c];
+    if (pr) a += pr[c];
+    v[n] = a;
+    s += a;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / C, q = 0.f;
+  for (int i = 0; i < n; ++i) { float d = v[i] - mean; q = fmaf(d, d, q); }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  float rstd = 1.0f / sqrtf(q / C + eps);
+  float* yr = y.row(b, t);
+  const float* rr = has_res ? res.row(b, t) : nullptr;
+  n = 0;
+  for (int c = lane; c < C; c += 32, ++n) {
+    float o = (v[n] - mean) * rstd * g[c] + bta[c];
+    if (rr) o += rr[c];
+    if (act == ACT_RELU) o = o > 0.f ? o : 0.f;
+    yr[c] = o;
+  }
+}
+static void ln_pre(ts_engine* e, const Act3& x, const Act3* pre, const float* g, const float* b, const Act3& y, const Act3* res,
+                   int act, cudaStream_t s) {
+  if (e->ws.sizing) return;
+  if (x.C > 768) fail(TS_ERR_INVALID, "layernorm width %d > 768", x.C);
+  int rows = x.B * x.T;
+  ln_pre_kernel<<<cdiv(rows, 8), 256, 0, s>>>(x, pre ? *pre : Act3(), pre ? 1 : 0, g, b, y, res ? *res : Act3(), res ? 1 : 0, act, 1e-5f);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+}
+
+// id_mlp: Conv1d(ncls,64,1) on the id vector, broadcast over time into columns [off, off+64) of x
+__global__ void id_cols_kernel(const float* __restrict__ idv, const float* __restrict__ w, const float* __restrict__ bias, int ncls,
+                               Act3 x, int off) {
+  int b = blockIdx.y;
+  __shared__ float v[64];
+  if (threadIdx.x < 64) {
+    float a = bias[threadIdx.x];
+    for (int k = 0; k < ncls; ++k) a = fmaf(w[threadIdx.x * ncls + k], idv[b * ncls + k], a);
+    v[threadIdx.x] = a;
+  }
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < x.T * 64; i += gridDim.x * blockDim.x)
+    x.row(b, i / 64)[off + (i & 63)] = v[i & 63];
+}
+
+// multi-head self-attention, eager softmax(QK^T * scale) V, head_dim 64.  qkv rows are
+// [q(768) | k(768) | v(768)], head h uses columns h*64.. in each block.  One CTA = QT queries of one
+// (batch, head); scores for the QT rows live in shared memory.
+template <int QT>
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int H, float scale) {
+  extern __shared__ float sm[];
+  const int Tp = (T + 63) & ~63;
+  float* Qs = sm;                    // [QT][65]
+  float* KVs = Qs + QT * 65;         // [64][65]
+  float* S = KVs + 64 * 65;          // [QT][Tp]
+  const int bh = blockIdx.y, b = bh / H, h = bh % H;
+  const int q0 = blockIdx.x * QT, tid = threadIdx.x;
+  const int ld = 3 * H * 64;
+  const float* base = qkv + (size_t)b * T * ld;
+  constexpr int RQ = QT / 16;        // query rows per thread
+  const int ty = tid >> 4, tx = tid & 15;
+  for (int i = tid; i < QT * 64; i += 256) {
+    int r = i >> 6, d = i & 63;
+    Qs[r * 65 + d] = (q0 + r < T) ? base[(size_t)(q0 + r) * ld + h * 64 + d] : 0.f;
+  }
+  // phase 1: scores
+  for (int k0 = 0; k0 < T; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) {
+      int r = i >> 6, d = i & 63;
+      KVs[r * 65 + d] = (k0 + r < T) ? base[(size_t)(k0 + r) * ld + H * 64 + h * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    float acc[RQ][4];
+#pragma unroll
+    for (int i = 0; i < RQ; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int d = 0; d < 64; ++d) {
+      float q[RQ], k[4];
+#pragma unroll
+      for (int i = 0; i < RQ; ++i) q[i] = Qs[(ty * RQ + i) * 65 + d];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = KVs[(tx * 4 + j) * 65 + d];
+#pragma unroll
+      for (int i = 0; i < RQ; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(q[i], k[j], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < RQ; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int kk = k0 + tx * 4 + j;
+        S[(ty * RQ + i) * Tp + kk] = kk < T ? acc[i][j] * scale : -INFINITY;
+      }
+  }
+  __syncthreads();
+  // phase 2: softmax per row (warp per row)
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < QT; r += 8) {
+    float* row = S + r * Tp;
+    float mx = -INFINITY;
+    for (int k = lane; k < T; k += 32) mx = fmaxf(mx, row[k]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int k = lane; k < T; k += 32) { float ev = expf(row[k] - mx); row[k] = ev; sum += ev; }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int k = lane; k < Tp; k += 32) row[k] = k < T ? row[k] / sum : 0.f;
+  }
+  // phase 3: O = P V
+  float o[RQ][4];
+#pragma unroll
+  for (int i = 0; i < RQ; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  for (int k0 = 0; k0 < T; k0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * 64; i += 256) {
+      int r = i >> 6, d = i & 63;
+      KVs[r * 65 + d] = (k0 + r < T) ? base[(size_t)(k0 + r) * ld + 2 * H * 64 + h * 64 + d] : 0.f;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < 64; ++kk) {
+      float p[RQ], v[4];
+#pragma unroll
+      for (int i = 0; i < RQ; ++i) p[i] = S[(ty * RQ + i) * Tp + k0 + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = KVs[kk * 65 + tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < RQ; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(p[i], v[j], o[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < RQ; ++i) {
+    int q = q0 + ty * RQ + i;
+    if (q < T)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) out[((size_t)b * T + q) * (H * 64) + h * 64 + tx * 4 + j] = o[i][j];
+  }
+}
+
+static void attention(ts_engine* e, const float* qkv, float* out, int B, int T, int H, cudaStream_t s) {
+  if (e->ws.sizing) return;
+  const int Tp = (T + 63) & ~63;
+  auto smem = [&](int QT) { return (size_t)(QT * 65 + 64 * 65 + QT * Tp) * sizeof(float); };
+  const float scale = 0.125f;  // head_dim ** -0.5
+  const size_t lim = 220 * 1024;
+  if (smem(64) <= lim) {
+    TS_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(64)));
+    attention_kernel<64><<<dim3(cdiv(T, 64), B * H), 256, smem(64), s>>>(qkv, out, T, H, scale);
+  } else if (smem(32) <= lim) {
+    TS_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(32)));
+    attention_kernel<32><<<dim3(cdiv(T, 32), B * H), 256, smem(32), s>>>(qkv, out, T, H, scale);
+  } else if (smem(16) <= lim) {
+    TS_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(16)));
+    attention_kernel<16><<<dim3(cdiv(T, 16), B * H), 256, smem(16), s>>>(qkv, out, T, H, scale);
+  } else {
+    fail(TS_ERR_UNSUPPORTED, "attention: %d frames exceed the shared-memory score tile (max ~3000 frames = 100 s)", T);
+  }
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+}
+
+// plain GEMM on channel-last activations: y[:, coff:coff+N] = act(x W^T + b (+ res))
+static void linear(ts_engine* e, const Layer& L, const Act3& x, const Act3& y, int act, const Act3* res, cudaStream_t s, int coff = 0) {
+  if (L.K != x.C) fail(TS_ERR_INVALID, "linear: K %d vs C %d", L.K, x.C);
+  GemmP p;
+  p.A = x.row(0, 0); p.W = L.W; p.bias = L.bias; p.C = y.row(0, 0) + coff;
+  p.M = x.B * x.T; p.N = L.N; p.K = L.K; p.mper = x.T;
+  p.a_bs = x.bstride(); p.a_rs = x.C; p.kc = L.K; p.a_ts = L.K;
+  p.c_bs = y.bstride(); p.c_rs = y.C; p.act = act; p.ldw = L.K;
+  if (res) { p.R = res->row(0, 0); p.r_bs = res->bstride(); p.r_rs = res->C; }
+  launch_gemm(e, p, s);
+}
+
+static void face_run(ts_engine* e, const float* wave, const float* idv, float* out, int B, int N, int frame, cudaStream_t s) {
+  FaceNet& F = *e->face;
+  // ---- wav2vec2 feature extractor ---------------------------------------------------------
+  int T = (N - 10) / 5 + 1;
+  double* stats = e->ws.alloc<double>((size_t)B * 512 * 2);
+  Act3 h = new_act(e, B, T, 512, 0, s);
+  if (!e->ws.sizing) {
+    TS_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 512 * 2 * sizeof(double), s));
+    conv0_stats_kernel<<<dim3(cdiv(T, 256), B), 256, 0, s>>>(wave, F.conv0_w, N, T, stats);
+    conv0_apply_kernel<<<dim3(cdiv(T, 64), B), 256, 0, s>>>(wave, F.conv0_w, stats, F.gn_g, F.gn_b, N, T, h.p);
+    e->launches += 2;
+    TS_CUDA(cudaGetLastError());
+  }
+  for (int i = 1; i < 7; ++i) {
+    int To = (T - W2V_K[i]) / W2V_S[i] + 1;
+    Act3 y = new_act(e, B, To, 512, 0, s);
+    conv1d(e, F.conv[i], h, W2V_K[i], W2V_S[i], 0, y, To, ACT_GELU, nullptr, s);
+    h = y;
+    T = To;
+  }
+  // ---- 50 -> 30 fps interpolation, feature projection ------------------------------------------
+  Act3 hi = new_act(e, B, frame, 512, 0, s);
+  if (!e->ws.sizing) {
+    long n = (long)B * frame * 512;
+    interp_kernel<<<(int)std::min<long>((n + 255) / 256, 148 * 16), 256, 0, s>>>(h, hi);
+    e->launches++;
+    TS_CUDA(cudaGetLastError());
+  }
+  ln_pre(e, hi, nullptr, F.fp_ln_g, F.fp_ln_b, hi, nullptr, ACT_NONE, s);
+  Act3 x = new_act(e, B, frame, 768, 64, s);            // padded for the k=128 positional conv
+  linear(e, F.fproj, hi, x, ACT_NONE, nullptr, s);
+  // ---- positional conv embedding (k=128, groups=16, pad 64, last output dropped) + LN -----------
+  Act3 pc = new_act(e, B, frame, 768, 0, s);
+  {
+    GemmP p;
+    p.A = x.row(0, -64); p.W = F.posconv.W; p.bias = F.posconv.bias; p.C = pc.row(0, 0);
+    p.M = B * frame; p.N = 48; p.K = 128 * 48; p.mper = frame;
+    p.a_bs = x.bstride(); p.a_rs = 768; p.kc = 48; p.a_ts = 768;
+    p.c_bs = pc.bstride(); p.c_rs = 768; p.act = ACT_GELU; p.ldw = 128 * 48;
+    p.groups = 16; p.a_goff = 48; p.w_goff = (long)48 * 128 * 48; p.n_goff = 48;
+    launch_gemm(e, p, s);
+  }
+  Act3 hcur = new_act(e, B, frame, 768, 0, s);
+  ln_pre(e, x, &pc, F.enc_ln_g, F.enc_ln_b, hcur, nullptr, ACT_NONE, s);
+  // ---- 12 post-LN transformer layers ------------------------------------------------------------
+  Act3 qkv = new_act(e, B, frame, 2304, 0, s);
+  Act3 att = new_act(e, B, frame, 768, 0, s);
+  Act3 t1 = new_act(e, B, frame, 768, 0, s);
+  Act3 ff = new_act(e, B, frame, 3072, 0, s);
+  for (auto& L : F.layers) {
+    linear(e, L.qkv, hcur, qkv, ACT_NONE, nullptr, s);
+    attention(e, qkv.p, att.p, B, frame, 12, s);
+    linear(e, L.out, att, t1, ACT_NONE, &hcur, s);                       // h + out_proj(attn)
+    ln_pre(e, t1, nullptr, L.ln1_g, L.ln1_b, hcur, nullptr, ACT_NONE, s);
+    linear(e, L.ff1, hcur, ff, ACT_GELU, nullptr, s);
+    linear(e, L.ff2, ff, t1, ACT_NONE, &hcur, s);                        // h + ffn(h)
+    ln_pre(e, t1, nullptr, L.ln2_g, L.ln2_b, hcur, nullptr, ACT_NONE, s);
+  }
+  // ---- audio_feature_map + id_mlp concat -> first_net -------------------------------------------------
+  Act3 cat = new_act(e, B, frame, 320, 1, s);
+  linear(e, F.feat_map, hcur, cat, ACT_NONE, nullptr, s, 0);
+  if (!e->ws.sizing) {
+    id_cols_kernel<<<dim3(cdiv(frame * 64, 256), B), 256, 0, s>>>(idv, F.id_w, F.id_b, F.ncls, cat, 256);
+    e->launches++;
+    TS_CUDA(cudaGetLastError());
+  }
+  Act3 c0 = new_act(e, B, frame, 256, 0, s), r0 = new_act(e, B, frame, 256, 0, s);
+  conv1d(e, F.fn_conv[0], cat, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
+  conv1d(e, F.fn_res0, cat, 3, 1, 1, r0, frame, ACT_NONE, nullptr, s);
+  Act3 f = new_act(e, B, frame, 256, 1, s);
+  ln_pre(e, c0, nullptr, F.fn_g[0], F.fn_b[0], f, &r0, ACT_RELU, s);       // relu(LN(conv(x)) + conv_res(x))
+  for (int i = 1; i < 3; ++i) {
+    conv1d(e, F.fn_conv[i], f, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
+    Act3 g = new_act(e, B, frame, 256, 1, s);
+    ln_pre(e, c0, nullptr, F.fn_g[i], F.fn_b[i], g, &f, ACT_RELU, s);      // relu(LN(conv(x)) + x)
+    f = g;
+  }
+  // ---- two decoder branches -> [B, frame, 103] --------------------------------------------------------
+  Act3 yout;
+  yout.p = out; yout.B = B; yout.T = frame; yout.C = F.jaw_dim + F.exp_dim; yout.pad = 0;
+  for (int br = 0; br < 2; ++br) {
+    int c = br ? 256 : 64;
+    Act3 m = f;
+    for (int i = 0; i < 3; ++i) {
+      Act3 cc = new_act(e, B, frame, c, 0, s);
+      conv1d(e, F.dec_conv[br][i], m, 3, 1, 1, cc, frame, ACT_NONE, nullptr, s);
+      Act3 nn = new_act(e, B, frame, c, 1, s);
+      ln_pre(e, cc, nullptr, F.dec_g[br][i], F.dec_b[br][i], nn, nullptr, ACT_RELU, s);
+      m = nn;
+    }
+    linear(e, F.fin[br], m, yout, ACT_NONE, nullptr, s, br ? F.jaw_dim : 0);
+  }
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
+  TS_API_BEGIN(e)
+  Ckpt ck(tensors, n);
+  FaceNet* F = new FaceNet();
+  const std::string a = "audio_encoder.";
+  F->conv0_w = up(e, ck.f32(a + "feature_extractor.conv_layers.0.conv.weight", {512, 1, 10}), 5120);
+  F->gn_g = up(e, ck.f32(a + "feature_extractor.conv_layers.0.layer_norm.weight", {512}), 512);
+  F->gn_b = up(e, ck.f32(a + "feature_extractor.conv_layers.0.layer_norm.bias", {512}), 512);
+  for (int i = 1; i < 7; ++i)
+    F->conv[i] = pack_ckc(e, ck.f32(a + "feature_extractor.conv_layers." + std::to_string(i) + ".conv.weight", {512, 512, W2V_K[i]}),
+                          nullptr, 512, 512, W2V_K[i]);
+  F->fp_ln_g = up(e, ck.f32(a + "feature_projection.layer_norm.weight", {512}), 512);
+  F->fp_ln_b = up(e, ck.f32(a + "feature_projection.layer_norm.bias", {512}), 512);
+  F->fproj = pack_linear(e, ck.f32(a + "feature_projection.projection.weight", {768, 512}),
+                         ck.f32(a + "feature_projection.projection.bias", {768}), 768, 512);
+  const std::string en = a + "encoder.";
+  F->posconv = pack_ckc(e, ck.f32(en + "pos_conv_embed.conv.weight", {768, 48, 128}), ck.f32(en + "pos_conv_embed.conv.bias", {768}),
+                        768, 48, 128);
+  F->enc_ln_g = up(e, ck.f32(en + "layer_norm.weight", {768}), 768);
+  F->enc_ln_b = up(e, ck.f32(en + "layer_norm.bias", {768}), 768);
+  for (int l = 0; ck.has(en + "layers." + std::to_string(l) + ".attention.q_proj.weight"); ++l) {
+    const std::string p = en + "layers." + std::to_string(l) + ".";
+    EncLayer L;
+    std::vector<float> W((size_t)2304 * 768), Bv(2304);
+    const char* nm[3] = {"q_proj", "k_proj", "v_proj"};
+    for (int j = 0; j < 3; ++j) {
+      const float* w = ck.f32(p + "attention." + nm[j] + ".weight", {768, 768});
+      const float* b = ck.f32(p + "attention." + nm[j] + ".bias", {768});
+      std::copy(w, w + (size_t)768 * 768, W.begin() + (size_t)j * 768 * 768);
+      std::copy(b, b + 768, Bv.begin() + j * 768);
+    }
+    L.qkv.N = 2304; L.qkv.K = 768; L.qkv.taps = 1; L.qkv.cin = 768;
+    L.qkv.W = e->upload(W);
+    L.qkv.bias = e->upload(Bv);
+    L.out = pack_linear(e, ck.f32(p + "attention.out_proj.weight", {768, 768}), ck.f32(p + "attention.out_proj.bias", {768}), 768, 768);
+    L.ln1_g = up(e, ck.f32(p + "layer_norm.weight", {768}), 768);
+    L.ln1_b = up(e, ck.f32(p + "layer_norm.bias", {768}), 768);
+    L.ff1 = pack_linear(e, ck.f32(p + "feed_forward.intermediate_dense.weight", {3072, 768}),
+                        ck.f32(p + "feed_forward.intermediate_dense.bias", {3072}), 3072, 768);
+    L.ff2 = pack_linear(e, ck.f32(p + "feed_forward.output_dense.weight", {768, 3072}),
+                        ck.f32(p + "feed_forward.output_dense.bias", {768}), 768, 3072);
+    L.ln2_g = up(e, ck.f32(p + "final_layer_norm.weight", {768}), 768);
+    L.ln2_b = up(e, ck.f32(p + "final_layer_norm.bias", {768}), 768);
+    F->layers.push_back(L);
+  }
+  if (F->layers.empty()) fail(TS_ERR_MISSING, "face: no transformer layers in checkpoint");
+  F->feat_map = pack_linear(e, ck.f32("audio_feature_map.weight", {256, 768}), ck.f32("audio_feature_map.bias", {256}), 256, 768);
+  const ts_tensor* idw = ck.get("audio_middle.id_mlp.weight");
+  F->ncls = (int)idw->shape[1];
+  F->id_w = up(e, ck.f32("audio_middle.id_mlp.weight", {64, F->ncls, 1}), (size_t)64 * F->ncls);
+  F->id_b = up(e, ck.f32("audio_middle.id_mlp.bias", {64}), 64);
+  const std::string fn = "audio_middle.first_net.conv_layers.";
+  F->fn_res0 = pack_ckc(e, ck.f32(fn + "0.residual_layer.0.weight", {256, 320, 3}), ck.f32(fn + "0.residual_layer.0.bias", {256}), 256, 320, 3);
+  for (int i = 0; i < 3; ++i) {
+    int cin = i == 0 ? 320 : 256;
+    const std::string p = fn + std::to_string(i) + ".";
+    F->fn_conv[i] = pack_ckc(e, ck.f32(p + "conv.weight", {256, cin, 3}), ck.f32(p + "conv.bias", {256}), 256, cin, 3);
+    F->fn_g[i] = up(e, ck.f32(p + "norm.weight", {256}), 256);
+    F->fn_b[i] = up(e, ck.f32(p + "norm.bias", {256}), 256);
+  }
+  const ts_tensor* f0 = ck.get("final_out.0.weight");
+  const ts_tensor* f1 = ck.get("final_out.1.weight");
+  F->jaw_dim = (int)f0->shape[0];
+  F->exp_dim = (int)f1->shape[0];
+  for (int br = 0; br < 2; ++br) {
+    int c = br ? 256 : 64;
+    for (int i = 0; i < 3; ++i) {
+      int cin = i == 0 ? 256 : c;
+      const std::string p = "decoder." + std::to_string(br) + "." + std::to_string(i) + ".";
+      F->dec_conv[br][i] = pack_ckc(e, ck.f32(p + "conv.weight", {c, cin, 3}), ck.f32(p + "conv.bias", {c}), c, cin, 3);
+      F->dec_g[br][i] = up(e, ck.f32(p + "norm.weight", {c}), c);
+      F->dec_b[br][i] = up(e, ck.f32(p + "norm.bias", {c}), c);
+    }
+    int od = br ? F->exp_dim : F->jaw_dim;
+    const std::string p = "final_out." + std::to_string(br) + ".";
+    F->fin[br] = pack_ckc(e, ck.f32(p + "weight", {od, c, 1}), ck.f32(p + "bias", {od}), od, c, 1);
+  }
+  delete e->face;
+  e->face = F;
+  TS_API_END(e)
+}
+
+extern "C" int ts_face_forward(ts_engine* e, const float* wave, const float* id, float* out, int B, int N, int frame, void* stream) {
+  TS_API_BEGIN(e)
+  if (!e->face) fail(TS_ERR_NOT_LOADED, "face weights not loaded");
+  if (B <= 0 || N < 400 || frame <= 0) fail(TS_ERR_INVALID, "ts_face_forward: B=%d N=%d frame=%d (need >= 400 samples)", B, N, frame);
+  cudaStream_t s = (cudaStream_t)stream;
+  e->ws.begin_sizing();
+  face_run(e, wave, id, out, B, N, frame, s);
+  size_t need = e->ws.need;
+  e->ws.buf.ensure(need + 256);
+  e->ws.begin(need);
+  face_run(e, wave, id, out, B, N, frame, s);
+  TS_API_END(e)
 }

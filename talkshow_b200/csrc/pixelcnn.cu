@@ -719,7 +719,9 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
+    if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
     TS_CUDA(cudaLaunchCooperativeKernel((void*)pixelcnn_kernel<true>, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
+    if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
     e->launches++;
   } else {
     TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
@@ -754,6 +756,29 @@ extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
 }
 
 extern "C" int64_t ts_pixelcnn_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->row_bytes : 0; }
+extern "C" int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->staged_row_bytes : 0; }
+
+// CUDA-event timing of the persistent kernel on its launch stream (bench.py roofline leg).
+extern "C" int ts_pixelcnn_timing(ts_engine* e, int enable) {
+  TS_API_BEGIN(e)
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  PixelPlan* P = e->pix;
+  if (enable && !P->ev0) {
+    TS_CUDA(cudaEventCreate(&P->ev0));
+    TS_CUDA(cudaEventCreate(&P->ev1));
+  }
+  P->timing = enable != 0;
+  P->pending = false;
+  TS_API_END(e)
+}
+// duration (ms) of the most recent timed persistent-kernel launch; synchronises on its end event.
+extern "C" double ts_pixelcnn_last_ms(ts_engine* e) {
+  if (!e || !e->pix || !e->pix->pending) return -1.0;
+  float ms = 0.f;
+  if (cudaEventSynchronize(e->pix->ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, e->pix->ev0, e->pix->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
 
 extern "C" int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len) {
   TS_API_BEGIN(e)

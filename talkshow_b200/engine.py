@@ -62,6 +62,16 @@ class Engine:
     def pixelcnn_row_bytes(self):
         return int(self.L.ts_pixelcnn_row_bytes(self.h))
 
+    @property
+    def pixelcnn_staged_row_bytes(self):
+        return int(self.L.ts_pixelcnn_staged_row_bytes(self.h))
+
+    def pixelcnn_timing(self, enable=True):
+        self._check(self.L.ts_pixelcnn_timing(self.h, int(enable)), "ts_pixelcnn_timing")
+
+    def pixelcnn_last_ms(self):
+        return float(self.L.ts_pixelcnn_last_ms(self.h))
+
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
 

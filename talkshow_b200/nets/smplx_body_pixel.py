@@ -1,0 +1,120 @@
+"""s2g_body_pixel — host mirror of the reference wrapper nets/smplx_body_pixel.py (inference
+methods).  Audio features -> AudioEncoder -> gated-PixelCNN sampler -> two VQ-VAE decoders, all
+inside the CUDA engine (C ABI: ts_body_generate / ts_pixelcnn_generate / ts_vq_decode)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from ..data_utils.utils import get_mfcc_ta, load_wav, mfcc_from_wave
+from .base import draw_sampler_noise, resolve_device, shared_engine, strip_module
+
+
+class TrainWrapper:
+    """Constructor/attribute surface of nets/smplx_body_pixel.py:30-75 (args.gpu, args.infer,
+    config.Data.pose.*, config.Model.{composition,bh_model,code_num,vq_path})."""
+
+    def __init__(self, args, config, engine=None):
+        self.args = args
+        self.config = config
+        self.device = resolve_device(self.args.gpu)
+        self.global_step = 0
+        self.convert_to_6d = self.config.Data.pose.convert_to_6d
+        self.expression = self.config.Data.pose.expression
+        self.epoch = 0
+        self.init_params()
+        self.num_classes = 4
+        self.audio = True
+        self.composition = self.config.Model.composition
+        self.bh_model = self.config.Model.bh_model
+        if self.convert_to_6d or not self.bh_model or not self.composition:
+            raise NotImplementedError("talkshow_b200 builds the shipped config/body_pixel.json geometry "
+                                      "(convert_to_6d=false, bh_model=true, composition=true)")
+        self.engine = engine or shared_engine(self.device)
+        self.noise_device = self.device      # 'cpu' reproduces the CPU reference's RNG stream
+        self.noise_per_step = True
+        # the reference loads the VQ-VAE checkpoint at construction (:59-62); honour it when present
+        vq_path = getattr(self.config.Model, "vq_path", None)
+        if vq_path and os.path.exists(vq_path):
+            ck = torch.load(vq_path, map_location="cpu")["generator"]
+            self.load_vq_state_dict(ck)
+
+    def init_params(self):
+        """nets/smplx_body_pixel.py:144-174 (3-D axis-angle layout): body 39 + hands 90."""
+        self.each_dim = [0, 39, 90, 100 if self.expression else 0]
+        self.dim_list = [0, 0, 0, 39, 129]
+        self.full_dim = 129
+        self.pose = 43
+
+    # -- checkpoints -----------------------------------------------------------------------------
+    def load_vq_state_dict(self, sd):
+        """{'g_body': ..., 'g_hand': ...} as saved by s2g_body_vq.state_dict()."""
+        self.engine.load_vq(0, strip_module(sd["g_body"]))
+        self.engine.load_vq(1, strip_module(sd["g_hand"]))
+
+    def load_state_dict(self, state_dict):
+        """ckpt['generator'] of a body-pixel checkpoint (nets/smplx_body_pixel.py:115-142)."""
+        sd = {k: (strip_module(v) if v is not None else None) for k, v in state_dict.items() if isinstance(v, dict) or v is None}
+        if "generator" in sd:
+            self.engine.load_pixelcnn(sd["generator"])
+        else:
+            self.engine.load_pixelcnn(strip_module(state_dict))
+        if sd.get("audioencoder") is not None:
+            self.engine.load_audioenc(sd["audioencoder"])
+
+    # -- inference -------------------------------------------------------------------------------
+    def _noise(self, T, B):
+        return draw_sampler_noise(T, B, self.noise_device, per_step=self.noise_per_step)
+
+    def infer_on_audio(self, aud_fn, initial_pose=None, norm_stats=None, exp=None, var=None, w_pre=False, rand=None,
+                       continuity=False, id=None, fps=15, sr=22000, B=1, am=None, am_sr=None, frame=0, **kwargs):
+        """(aud_fn) -> generated motion, numpy (B, F, 129).  Reference: :232-289."""
+        assert self.args.infer, "train mode"
+        if continuity:
+            return self._infer_continuity(aud_fn, id, fps, sr, B)
+        if torch.is_tensor(aud_fn) or isinstance(aud_fn, np.ndarray):
+            aud_feat = np.asarray(aud_fn, dtype=np.float32)          # already (M, 64) features
+        else:
+            aud_feat = get_mfcc_ta(aud_fn, sr=sr, fps=fps, smlpx=True, type="mfcc", am=am)
+        mfcc = torch.from_numpy(np.ascontiguousarray(aud_feat.T))[None].repeat(B, 1, 1)       # [B,64,M]
+        label = torch.tensor([0]) if id is None else id.reshape(-1).repeat(B)[:B] if id.numel() == 1 else id
+        return self.generate(mfcc, label).cpu().numpy()
+
+    def generate(self, aud, id, frame_num=0):
+        """tensor API (:306-326): aud [B,64,M] features, id [B] -> torch (B, F, 129) on the device.
+        (The reference's version passes decode()'s tuple to torch.cat and raises; this returns the
+        tensor its infer_on_audio builds.)"""
+        mfcc = aud.to(torch.float32)
+        B, _, M = mfcc.shape
+        T = self.engine.latent_rows(M)
+        noise = self._noise(T, B)
+        codes, poses = self.engine.body_generate(mfcc, id.to(torch.int64), noise)
+        self.last_codes = codes
+        return poses
+
+    def _infer_continuity(self, aud_fn, id, fps, sr, B):
+        """continuity=True (:260-269): a 2 s prefix, then the rest conditioned on the prefix's latents
+        and audio (GatedPixelCNN.generate(pre_latents, pre_audio))."""
+        audio, sr_0 = load_wav(aud_fn)
+        import torchaudio.transforms as ta_T
+        if sr != sr_0:
+            audio = ta_T.Resample(sr_0, sr)(audio)
+            sr_0 = sr
+        if audio.shape[0] > 1:
+            audio = torch.mean(audio, dim=0, keepdim=True)
+        cut = 2 * sr
+        f0 = mfcc_from_wave(audio[:, :cut], sr_0, sr=sr, fps=fps)        # get_mfcc_sepa, utils.py:234-263
+        f1 = mfcc_from_wave(audio[:, cut:], sr_0, sr=sr, fps=fps)
+        label = (torch.tensor([0]) if id is None else id.reshape(-1)).repeat(B)[:B]
+        m0 = torch.from_numpy(np.ascontiguousarray(f0.T))[None].repeat(B, 1, 1)
+        m1 = torch.from_numpy(np.ascontiguousarray(f1.T))[None].repeat(B, 1, 1)
+        a0, a1 = self.engine.audio_encode(m0), self.engine.audio_encode(m1)
+        T0, T1 = a0.shape[2], a1.shape[2]
+        lat0 = self.engine.pixelcnn_generate(a0, label, self._noise(T0, B))
+        lat1 = self.engine.pixelcnn_generate(torch.cat([a0, a1], 2), label, self._noise(T1, B), T=T1, pre_latents=lat0)
+        lat = torch.cat([lat0, lat1], 1)
+        body = self.engine.vq_decode(0, lat[..., 0].contiguous())
+        hand = self.engine.vq_decode(1, lat[..., 1].contiguous())
+        return torch.cat([body, hand], 1).transpose(1, 2).cpu().numpy()

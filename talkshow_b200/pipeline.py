@@ -1,0 +1,84 @@
+"""Whole-body batch generation (what scripts/demo.py:158-229 does per clip, batched) and its
+multi-GPU sharding.
+
+A batch of clips / diversity samples is a set of independent autoregressive chains:
+rank r of G takes a contiguous slice of the batch, runs face + body + pose assembly on its own
+GPU, and ONE NCCL all-gather of the final [b,F,265] pose tensor rebuilds the batch on every rank.
+No other collective is on the path.
+"""
+from __future__ import annotations
+
+import torch
+
+from .engine import Engine
+from .nets.base import draw_sampler_noise
+
+
+def shard_range(B, rank, world):
+    """Contiguous slice of the batch owned by ``rank`` (first B % world ranks get one extra)."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class WholeBody:
+    """face (jaw+expression) + body/hands + part2full assembly -> SMPL-X parameters [B,F,265]."""
+
+    def __init__(self, engine: Engine):
+        self.e = engine
+        self.device = engine.device
+
+    def load(self, pixel_ckpt, vq_ckpt, face_ckpt):
+        """Checkpoint dicts in the reference's formats (talkshow_b200/synth.py docstring)."""
+        self.e.load_pixelcnn(pixel_ckpt["generator"])
+        self.e.load_audioenc(pixel_ckpt["audioencoder"])
+        self.e.load_vq(0, vq_ckpt["g_body"])
+        self.e.load_vq(1, vq_ckpt["g_hand"])
+        self.e.load_face(face_ckpt["generator"])
+
+    def generate(self, mfcc, wave, label, noise=None, stand=False, per_step_noise=True):
+        """mfcc [B,64,M], wave [B,N] (16 kHz), label [B] on the device -> poses [B,F,265] (device).
+        F = N*30//16000 face frames; the body (4*T frames) is padded/truncated to F like demo.py:207-211."""
+        B, _, M = mfcc.shape
+        frame = wave.shape[1] * 30 // 16000
+        T = self.e.latent_rows(M)
+        if noise is None:
+            noise = draw_sampler_noise(T, B, self.device, per_step=per_step_noise)
+        face = self.e.face_forward(wave, torch.zeros(B, 4, device=self.device), frame)   # demo.py:173-181: id not passed
+        _, body = self.e.body_generate(mfcc, label, noise, want_codes=False)
+        return self.e.assemble_pose(face, body, stand)
+
+    def generate_host(self, mfcc_host, wave_host, label_host, out_host=None, **kw):
+        """Public end-to-end call with HOST buffers (pinned for async copies): H2D inputs, generate,
+        D2H result.  Returns the host tensor [B,F,265]."""
+        mfcc = mfcc_host.to(self.device, non_blocking=True)
+        wave = wave_host.to(self.device, non_blocking=True)
+        label = label_host.to(self.device, non_blocking=True)
+        poses = self.generate(mfcc, wave, label, **kw)
+        if out_host is None:
+            out_host = torch.empty(poses.shape, dtype=poses.dtype, pin_memory=True)
+        out_host.copy_(poses, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host
+
+
+def allgather_poses(local, B_total, world, group=None):
+    """ONE all-gather of the pose tensor over NCCL (NVLink/NVSwitch).  local [b,F,265] -> [B_total,F,265].
+    Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""
+    import torch.distributed as dist
+
+    if world == 1:
+        return local
+    bmax = -(-B_total // world)
+    if local.shape[0] < bmax:
+        pad = torch.zeros((bmax - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], 0)
+    out = torch.empty((world * bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    if B_total == world * bmax:
+        return out
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(B_total, r, world)
+        parts.append(out[r * bmax: r * bmax + (hi - lo)])
+    return torch.cat(parts, 0)

@@ -183,3 +183,43 @@ def test_assemble_pose(eng):
         assert torch.equal(got[b], O.assemble_pose(face[b], body[b]))
     got = eng.assemble_pose(face, body, stand=True).cpu()
     assert torch.equal(got[1], O.assemble_pose(face[1], body[1], stand=True))
+
+
+@pytest.fixture(scope="module")
+def face_eng(ckpts):
+    from talkshow_b200.engine import Engine
+
+    e = Engine(0)
+    e.load_face(ckpts["face"]["generator"])
+    yield e
+    torch.cuda.synchronize()
+    e.close()
+
+
+def test_face_golden_4s(face_eng, ckpts):
+    """BASELINE config 1 stand-in: 4 s clip, id=None (zeros), reference-generated golden, 1e-4 bar."""
+    gold = _load("face")
+    wave = synth.synth_wave(1, 64000)
+    got = face_eng.face_forward(wave, torch.zeros(1, 4), 64000 * 30 // 16000).cpu().numpy()
+    err = np.abs(got - gold["out_4s"]).max()
+    print("face 4 s max-abs err vs reference golden: %.3e" % err)
+    assert got.shape == (1, 120, 103)
+    assert err <= TOL
+
+
+def test_face_batch_ids(face_eng, ckpts):
+    gold = _load("face")
+    wave2 = synth.synth_wave(2, 24000, seed=5)
+    ids = torch.nn.functional.one_hot(torch.tensor(gold["ids_b2"]), 4).float()
+    got = face_eng.face_forward(wave2, ids, 45).cpu().numpy()
+    assert np.abs(got - gold["out_b2"]).max() <= TOL
+
+
+def test_face_vs_oracle_10s(face_eng, ckpts):
+    wave = synth.synth_wave(2, 160000, seed=8)
+    ids = torch.nn.functional.one_hot(torch.tensor([2, 0]), 4).float()
+    ref = O.face_forward(ckpts["face"]["generator"], wave, ids, 300)
+    got = face_eng.face_forward(wave, ids, 300).cpu()
+    err = (got - ref).abs().max().item()
+    print("face 10 s max-abs err vs oracle: %.3e" % err)
+    assert err <= TOL
