@@ -1,0 +1,377 @@
+// talkshow_b200 — tensor-core implicit-GEMM for the dense contractions (face wav2vec2 convs /
+// transformer, VQ decoder convs): tcgen05.mma kind::tf32 with fp32-grade accuracy by the 3xTF32
+// split  x = hi + lo,  A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (fp32 accumulate in TMEM).
+//
+//  * operands arrive pre-split (hi = fp32 with the 13 low mantissa bits cleared, lo = x - hi, exact)
+//    as K-major tiles: TMA (cp.async.bulk.tensor, 128B swizzle) stages [128 x 32] fp32 boxes of
+//    A_hi, A_lo, W_hi, W_lo per k-block into a 3-stage shared-memory ring;
+//  * one elected thread issues 12 tcgen05.mma (4 k-steps x 3 products) per stage into a 128x128 fp32
+//    accumulator in TMEM; tcgen05.commit releases the stage / publishes the accumulator;
+//  * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), add bias / residual, apply the activation and
+//    write either plain fp32 or the (hi, lo) pair the next tensor-core GEMM consumes.
+//  A Conv1d(k, stride s) is the same kernel: the A tensor map is 3-D {C, s, rows/s} over the padded
+//  channel-last buffer, tap t reads box (c0, t % s, j + t / s); GEMM rows are indexed by the padded row
+//  index j, rows that fall on padding are computed and discarded by the epilogue.
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace ts {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;                             // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+
+struct TcArgs {
+  int taps, cblocks, stride;        // K loop = taps x (C / 32)
+  int C;                            // input channels (K per tap)
+  int rows_in, off, T_out, nbatch;  // epilogue row mapping (see header)
+  int Rs;                           // GEMM rows (padded row index / stride)
+  int N;
+  float* c_hi;                      // output (plain fp32 when c_lo == nullptr)
+  float* c_lo;
+  long c_bs, c_rs;
+  const float* bias;
+  const float* r_hi;                // residual: plain (r_lo null) or split
+  const float* r_lo;
+  long r_bs, r_rs;
+  int act;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, int c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(c)); }
+__device__ __forceinline__ void mb_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nTCW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TCD;\nbra TCW;\nTCD:\n}\n" ::"r"(s_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s_u32(dst)),
+               "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s_u32(dst)),
+               "l"(m), "r"(c0), "r"(c1), "r"(s_u32(bar))
+               : "memory");
+}
+// K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (=1), version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a), "l"(b),
+      "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
+  if (act == ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+               const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* tmem_full = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  const int nk = P.taps * P.cblocks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    mb_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_lo) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        mb_wait(&empty[st], ph ^ 1);
+        const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
+        unsigned char* base = smem + st * TC_STAGE_BYTES;
+        mb_expect(&full[st], TC_STAGE_BYTES);
+        const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
+        tma_3d(base, &mA_hi, c0, c1, c2, &full[st]);
+        tma_3d(base + TC_TILE_BYTES, &mA_lo, c0, c1, c2, &full[st]);
+        const int kcol = tap * P.C + cb * TC_BK;
+        tma_2d(base + 2 * TC_TILE_BYTES, &mB_hi, kcol, n0, &full[st]);
+        tma_2d(base + 3 * TC_TILE_BYTES, &mB_lo, kcol, n0, &full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      // instruction descriptor: D=F32, A=B=TF32, K-major both, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        mb_wait(&full[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = s_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES,
+                       b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t o = k * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom
+          umma_tf32(tmem_base, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+          umma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+        }
+        umma_commit(&empty[st]);   // stage reusable once these MMAs have read it
+      }
+      umma_commit(tmem_full);      // accumulator complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int j = j0 + row;
+    // GEMM row j <-> padded input row j*stride -> (batch, output step)
+    bool valid = j < P.Rs;
+    int b = 0, t = 0;
+    if (valid) {
+      long in_row = (long)j * P.stride;
+      b = (int)(in_row / P.rows_in);
+      int tin = (int)(in_row - (long)b * P.rows_in) - P.off;
+      valid = b < P.nbatch && tin >= 0 && (tin % P.stride) == 0;
+      t = tin / P.stride;
+      valid = valid && t < P.T_out;
+    }
+    mb_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* crow_hi = P.c_hi + (long)b * P.c_bs + (long)t * P.c_rs;
+    float* crow_lo = P.c_lo ? P.c_lo + (long)b * P.c_bs + (long)t * P.c_rs : nullptr;
+    const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
+    const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
+#pragma unroll 1
+    for (int cc = 0; cc < TC_BN / 32; ++cc) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const int n = n0 + cc * 32 + q;
+          if (n >= P.N) break;
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x = __uint_as_float(v[q + u]);
+            if (n + u < P.N) {
+              if (P.bias) x += P.bias[n + u];
+              if (rrow_hi) x += rrow_lo ? (rrow_hi[n + u] + rrow_lo[n + u]) : rrow_hi[n + u];
+              x = tc_act(x, P.act);
+            }
+            o[u] = x;
+          }
+          if (n + 3 < P.N) {
+            if (crow_lo) {
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
+              h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
+              h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
+              h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
+              *reinterpret_cast<float4*>(crow_hi + n) = h;
+              *reinterpret_cast<float4*>(crow_lo + n) = l;
+            } else {
+              *reinterpret_cast<float4*>(crow_hi + n) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            for (int u = 0; u < 4 && n + u < P.N; ++u) {
+              if (crow_lo) {
+                float h = __uint_as_float(__float_as_uint(o[u]) & 0xffffe000u);
+                crow_hi[n + u] = h;
+                crow_lo[n + u] = o[u] - h;
+              } else {
+                crow_hi[n + u] = o[u];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN) : "memory");
+  }
+}
+
+// ---- split kernels ------------------------------------------------------------------------------
+__global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+void split_hi_lo(ts_engine* e, const float* x, float* hi, float* lo, long n, cudaStream_t s) {
+  if (e->ws.sizing || n <= 0) return;
+  split_kernel<<<(int)std::min<long>((n + 255) / 256, 148 * 16), 256, 0, s>>>(x, hi, lo, n);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+}
+void split_host(const std::vector<float>& w, std::vector<float>* hi, std::vector<float>* lo) {
+  hi->resize(w.size());
+  lo->resize(w.size());
+  for (size_t i = 0; i < w.size(); ++i) {
+    uint32_t u;
+    memcpy(&u, &w[i], 4);
+    u &= 0xffffe000u;
+    float h;
+    memcpy(&h, &u, 4);
+    (*hi)[i] = h;
+    (*lo)[i] = w[i] - h;
+  }
+}
+
+// ---- host launcher -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    TS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) fail(TS_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+static CUtensorMap make_map(const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  CUtensorMap m;
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(TS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu", (int)r, rank, (unsigned long long)dims[0],
+                              (unsigned long long)dims[1]);
+  return m;
+}
+
+bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd) {
+  if (!L.W_hi || !x.lo) return false;
+  if (x.C % TC_BK) return false;
+  const int rows_in = x.T + 2 * x.pad + x.tail;
+  if (rows_in % stride || (x.pad - pd) % stride || x.pad < pd) return false;
+  if ((reinterpret_cast<uintptr_t>(x.p) & 15) || ((long)x.C * 4 * stride) % 16) return false;
+  return true;
+}
+
+// y(b, t*y_tmul + y_toff, :) = act( conv(x)(b,t,:) + bias + res(b,t,:) );  x and W must be split (hi/lo)
+void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
+               cudaStream_t s, int y_tmul, int y_toff) {
+  if (e->ws.sizing) return;
+  if (!tc_conv_supported(L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
+  if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "tc_conv1d: layer/input mismatch");
+  const int rows_in = x.T + 2 * x.pad + x.tail;
+  const long R = (long)x.B * rows_in;
+  const long Rs = R / stride;
+  const float* base_hi = x.p;   // first padded row of batch 0 (Act3::p points at the allocation start)
+  const float* base_lo = x.lo;
+  cuuint64_t adims[3] = {(cuuint64_t)x.C, (cuuint64_t)stride, (cuuint64_t)Rs};
+  cuuint64_t astr[2] = {(cuuint64_t)x.C * 4, (cuuint64_t)x.C * 4 * stride};
+  cuuint32_t abox[3] = {TC_BK, 1, TC_BM};
+  CUtensorMap mAh = make_map(base_hi, 3, adims, astr, abox), mAl = make_map(base_lo, 3, adims, astr, abox);
+  cuuint64_t bdims[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
+  cuuint64_t bstr[1] = {(cuuint64_t)L.K * 4};
+  cuuint32_t bbox[2] = {TC_BK, TC_BN};
+  CUtensorMap mBh = make_map(L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(L.W_lo, 2, bdims, bstr, bbox);
+  TcArgs P;
+  P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
+  P.rows_in = rows_in; P.off = x.pad - pd; P.T_out = T_out; P.nbatch = x.B; P.Rs = (int)Rs; P.N = L.N;
+  P.c_hi = y.row(0, y_toff); P.c_lo = y.lo ? y.lo + (y.row(0, y_toff) - y.p) : nullptr;
+  P.c_bs = y.bstride(); P.c_rs = (long)y_tmul * y.C;
+  P.bias = L.bias;
+  P.r_hi = res ? res->row(0, 0) : nullptr;
+  P.r_lo = (res && res->lo) ? res->lo + (res->row(0, 0) - res->p) : nullptr;
+  P.r_bs = res ? res->bstride() : 0; P.r_rs = res ? res->C : 0;
+  P.act = act;
+  static bool attr = false;
+  if (!attr) { TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
+  dim3 grid((unsigned)((Rs + TC_BM - 1) / TC_BM), (unsigned)((L.N + TC_BN - 1) / TC_BN));
+  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mAh, mAl, mBh, mBl, P);
+  e->launches++;
+  TS_CUDA(cudaGetLastError());
+}
+
+}  // namespace ts
+
+using namespace ts;
+
+// debug entry: dense C[M,N] = act(A[M,K] W[N,K]^T + bias), mode 0 = FFMA kernel, 1 = tcgen05 3xTF32
+extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
+                             void* stream) {
+  TS_API_BEGIN(e)
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0) {
+    GemmP p;
+    p.A = A; p.W = W; p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.mper = M; p.a_rs = K; p.kc = K; p.a_ts = K; p.c_rs = N; p.act = act; p.ldw = K;
+    e->ws.sizing = false;
+    launch_gemm(e, p, s);
+  } else {
+    if (K % TC_BK) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 32 for the tensor-core path");
+    e->ws.sizing = false;
+    float *ah, *al, *wh, *wl;
+    TS_CUDA(cudaMalloc(&ah, (size_t)M * K * 4)); TS_CUDA(cudaMalloc(&al, (size_t)M * K * 4));
+    TS_CUDA(cudaMalloc(&wh, (size_t)N * K * 4)); TS_CUDA(cudaMalloc(&wl, (size_t)N * K * 4));
+    split_hi_lo(e, A, ah, al, (long)M * K, s);
+    split_hi_lo(e, W, wh, wl, (long)N * K, s);
+    Layer L;
+    L.N = N; L.K = K; L.taps = 1; L.cin = K; L.W_hi = wh; L.W_lo = wl; L.bias = const_cast<float*>(bias);
+    Act3 x; x.p = ah; x.lo = al; x.B = 1; x.T = M; x.C = K; x.pad = 0;
+    Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
+    tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0);
+    TS_CUDA(cudaStreamSynchronize(s));
+    cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+  }
+  TS_API_END(e)
+}
