@@ -120,6 +120,13 @@ double ts_pixelcnn_last_ms(ts_engine* e);
 /* Export the PixelCNN execution plan (stage table + packed weight blob) to host buffers so a test
  * can interpret it on the CPU; sizes are returned when the buffers are NULL. */
 int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len);
+/* dense C[M,N] = act(A[M,K] W[N,K]^T + bias) through one of the two GEMM kernels (unit tests):
+ * mode 0 = fp32 FFMA kernel, mode 1 = tcgen05 3xTF32 tensor-core kernel (K % 32 == 0). */
+int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N,
+                  int K, int act, void* stream);
+/* 1 (default): face / VQ-decoder contractions run on the tcgen05 3xTF32 tensor-core kernel;
+ * 0: everything on the fp32 FFMA kernel (A/B comparison in tests and profiles). */
+int ts_set_tensor_cores(ts_engine* e, int enable);
 /* 0 = persistent cooperative kernel (default), 1 = one launch per stage (debug cross-check) */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
 

@@ -109,6 +109,8 @@ struct Workspace {
 // (tap-major, channel-minor, Cin padded to a multiple of 4), bias [N].
 struct Layer {
   float* W = nullptr;
+  float* W_hi = nullptr;  // 3xTF32 split copies for the tensor-core path (gemm_tc.cu), optional
+  float* W_lo = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0, taps = 1, cin = 0;  // cin = padded input channels
 };
@@ -126,6 +128,7 @@ struct ts_engine {
   std::string err;
   int64_t launches = 0;
   int pixel_mode = 0;
+  bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows
   ts::PixelPlan* pix = nullptr;
   ts::ConvStacks* conv = nullptr;
   ts::FaceNet* face = nullptr;

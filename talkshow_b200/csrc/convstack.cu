@@ -62,7 +62,7 @@ static Layer pack_conv(ts_engine* e, const Ckpt& ck, const std::string& p, int c
   L.taps = k;
   L.cin = cp;
   L.K = k * cp;
-  L.W = e->upload(W);
+  upload_weights(e, W, &L);
   L.bias = e->upload(B);
   return L;
 }
@@ -81,7 +81,7 @@ static Layer pack_plain(ts_engine* e, const Ckpt& ck, const std::string& p, int 
   L.taps = k;
   L.cin = cp;
   L.K = k * cp;
-  L.W = e->upload(W);
+  upload_weights(e, W, &L);
   L.bias = e->upload(B);
   return L;
 }
@@ -110,7 +110,7 @@ static void pack_up(ts_engine* e, const Ckpt& ck, const std::string& p, int cin,
     L.taps = 2;
     L.cin = cin;
     L.K = 2 * cin;
-    L.W = e->upload(W);
+    upload_weights(e, W, &L);
     L.bias = e->upload(B);
     *(ph ? odd : even) = L;
   }
@@ -165,24 +165,29 @@ void pack_vq(ts_engine* e, const Ckpt& ck, VQNet* v) {
 }
 
 // ---- execution -------------------------------------------------------------------------------
-Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s) {
+Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool split, int tail) {
   Act3 a;
   a.B = B;
   a.T = T;
   a.C = C;
   a.pad = pad;
+  a.tail = tail;
+  a.split = split;
   a.p = e->ws.alloc<float>(a.numel());
+  if (split) a.lo = e->ws.alloc<float>(a.numel());
   zero_pads(e, a, s);
   return a;
 }
 
-static Act3 run_stack(ts_engine* e, const ResStack& st, const Act3& x, cudaStream_t s) {
-  Act3 h0 = new_act(e, x.B, x.T, x.C, 1, s);
-  conv1d(e, st.l0, x, 3, 1, 1, h0, x.T, ACT_LRELU, nullptr, s);
-  Act3 h1 = new_act(e, x.B, x.T, x.C, 1, s);
-  conv1d(e, st.l1, h0, 3, 1, 1, h1, x.T, ACT_LRELU, nullptr, s);
-  Act3 y = new_act(e, x.B, x.T, x.C, 1, s);
-  conv1d(e, st.fin, h1, 3, 1, 1, y, x.T, ACT_RELU, &x, s);  // relu(BN(conv(h)) + x), vqvae_modules.py:210-212
+static Act3 run_stack(ts_engine* e, const ResStack& st, const Act3& x, cudaStream_t s, bool tc = false) {
+  // tc: activations kept as (hi, lo) pairs so the convs run on the tensor-core kernel (VQ decoder);
+  // the audio / VQ encoders stay on the fp32 FFMA kernel (their outputs decide code indices)
+  Act3 h0 = new_act(e, x.B, x.T, x.C, 1, s, tc);
+  conv_auto(e, st.l0, x, 3, 1, 1, h0, x.T, ACT_LRELU, nullptr, s);
+  Act3 h1 = new_act(e, x.B, x.T, x.C, 1, s, tc);
+  conv_auto(e, st.l1, h0, 3, 1, 1, h1, x.T, ACT_LRELU, nullptr, s);
+  Act3 y = new_act(e, x.B, x.T, x.C, 1, s, tc);
+  conv_auto(e, st.fin, h1, 3, 1, 1, y, x.T, ACT_RELU, &x, s);  // relu(BN(conv(h)) + x), vqvae_modules.py:210-212
   return y;
 }
 
@@ -200,24 +205,25 @@ Act3 run_trunk(ts_engine* e, const Trunk& t, const Act3& x, cudaStream_t s) {
   return run_stack(e, t.s3, d2, s);
 }
 
-static Act3 run_up(ts_engine* e, const Layer& ev, const Layer& od, const Act3& x, cudaStream_t s) {
-  Act3 y = new_act(e, x.B, 2 * x.T, ev.N, 1, s);
-  conv1d(e, ev, x, 2, 1, 1, y, x.T, ACT_LRELU, nullptr, s, 2, 0, 0);   // rows m-1, m   -> y[2m]
-  conv1d(e, od, x, 2, 1, 0, y, x.T, ACT_LRELU, nullptr, s, 2, 1, 0);   // rows m, m+1   -> y[2m+1]
+static Act3 run_up(ts_engine* e, const Layer& ev, const Layer& od, const Act3& x, cudaStream_t s, bool tc) {
+  Act3 y = new_act(e, x.B, 2 * x.T, ev.N, 1, s, tc);
+  conv_auto(e, ev, x, 2, 1, 1, y, x.T, ACT_LRELU, nullptr, s, 2, 0);   // rows m-1, m   -> y[2m]
+  conv_auto(e, od, x, 2, 1, 0, y, x.T, ACT_LRELU, nullptr, s, 2, 1);   // rows m, m+1   -> y[2m+1]
   return y;
 }
 
 // q: quantised latents [B,T,64] channel-last -> decoder output Act3 [B,4T,C]
 Act3 run_decoder(ts_engine* e, const VQNet& v, const Act3& q, cudaStream_t s) {
-  Act3 h = new_act(e, q.B, q.T, 1024, 1, s);
-  conv1d(e, v.aft_vq, q, 1, 1, 0, h, q.T, ACT_NONE, nullptr, s);
-  h = run_stack(e, v.d1, h, s);
-  h = run_up(e, v.up2e, v.up2o, h, s);
-  h = run_stack(e, v.d2, h, s);
-  h = run_up(e, v.up3e, v.up3o, h, s);
-  h = run_stack(e, v.d3, h, s);
+  const bool tc = e->use_tc;
+  Act3 h = new_act(e, q.B, q.T, 1024, 1, s, tc);
+  conv_auto(e, v.aft_vq, q, 1, 1, 0, h, q.T, ACT_NONE, nullptr, s);
+  h = run_stack(e, v.d1, h, s, tc);
+  h = run_up(e, v.up2e, v.up2o, h, s, tc);
+  h = run_stack(e, v.d2, h, s, tc);
+  h = run_up(e, v.up3e, v.up3o, h, s, tc);
+  h = run_stack(e, v.d3, h, s, tc);
   Act3 y = new_act(e, q.B, h.T, pad4(v.out_dim), 0, s);
-  conv1d(e, v.project, h, 1, 1, 0, y, h.T, ACT_NONE, nullptr, s);
+  conv_auto(e, v.project, h, 1, 1, 0, y, h.T, ACT_NONE, nullptr, s);
   return y;
 }
 

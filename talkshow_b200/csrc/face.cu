@@ -52,14 +52,14 @@ static Layer pack_ckc(ts_engine* e, const float* w, const float* b, int cout, in
       for (int t = 0; t < k; ++t) W[((size_t)o * k + t) * cp + c] = w[((size_t)o * cin + c) * k + t];
   Layer L;
   L.N = cout; L.taps = k; L.cin = cp; L.K = k * cp;
-  L.W = e->upload(W);
+  upload_weights(e, W, &L);
   L.bias = b ? up(e, b, cout) : nullptr;
   return L;
 }
 static Layer pack_linear(ts_engine* e, const float* w, const float* b, int N, int K) {
   Layer L;
   L.N = N; L.K = K; L.taps = 1; L.cin = K;
-  L.W = up(e, w, (size_t)N * K);
+  upload_weights(e, std::vector<float>(w, w + (size_t)N * K), &L);
   L.bias = b ? up(e, b, N) : nullptr;
   return L;
 }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restric
 // recompute conv0, normalise per (b,c), affine, GELU, write channel-last [B,T0,512]
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wave, const float* __restrict__ w,
                                                           const double* __restrict__ stats, const float* __restrict__ g,
-                                                          const float* __restrict__ bta, int N, int T0, float* __restrict__ out) {
+                                                          const float* __restrict__ bta, int N, int T0, Act3 out) {
   constexpr int TC = 64;
   __shared__ float xs[TC * 5 + 16];
   const int b = blockIdx.y, t0 = blockIdx.x * TC, tid = threadIdx.x;
@@ -117,7 +117,13 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
       for (int j = 0; j < 10; ++j) y = fmaf(wr[j], xs[t * 5 + j], y);
       float v = (y - mu) * rstd * gg + bb;
       v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-      out[((size_t)b * T0 + t0 + t) * 512 + c] = v;
+      if (out.lo) {
+        float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        out.row(b, t0 + t)[c] = h;
+        out.row_lo(b, t0 + t)[c] = v - h;
+      } else {
+        out.row(b, t0 + t)[c] = v;
+      }
     }
   }
 }
@@ -148,12 +154,14 @@ __global__ void ln_pre_kernel(Act3 x, Act3 pre, int has_pre, const float* __rest
   if (warp >= rows) return;
   int b = warp / x.T, t = warp % x.T, C = x.C;
   const float* xr = x.row(b, t);
+  const float* xl = x.lo ? x.row_lo(b, t) : nullptr;
   const float* pr = has_pre ? pre.row(b, t) : nullptr;
   float v[24];  // C <= 768
   float s = 0.f;
   int n = 0;
   for (int c = lane; c < C; c += 32, ++n) {
     float a = xr[c];
+    if (xl) a += xl[c];
     if (pr) a += pr[c];
     v[n] = a;
     s += a;
@@ -164,13 +172,21 @@ __global__ void ln_pre_kernel(Act3 x, Act3 pre, int has_pre, const float* __rest
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   float rstd = 1.0f / sqrtf(q / C + eps);
   float* yr = y.row(b, t);
+  float* yl = y.lo ? y.row_lo(b, t) : nullptr;
   const float* rr = has_res ? res.row(b, t) : nullptr;
+  const float* rl = (has_res && res.lo) ? res.row_lo(b, t) : nullptr;
   n = 0;
   for (int c = lane; c < C; c += 32, ++n) {
     float o = (v[n] - mean) * rstd * g[c] + bta[c];
-    if (rr) o += rr[c];
+    if (rr) o += rl ? (rr[c] + rl[c]) : rr[c];
     if (act == ACT_RELU) o = o > 0.f ? o : 0.f;
-    yr[c] = o;
+    if (yl) {
+      float h = __uint_as_float(__float_as_uint(o) & 0xffffe000u);
+      yr[c] = h;
+      yl[c] = o - h;
+    } else {
+      yr[c] = o;
+    }
   }
 }
 static void ln_pre(ts_engine* e, const Act3& x, const Act3* pre, const float* g, const float* b, const Act3& y, const Act3* res,
@@ -202,7 +218,8 @@ __global__ void id_cols_kernel(const float* __restrict__ idv, const float* __res
 // [q(768) | k(768) | v(768)], head h uses columns h*64.. in each block.  One CTA = QT queries of one
 // (batch, head); scores for the QT rows live in shared memory.
 template <int QT>
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int H, float scale) {
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ out_lo, int T,
+                                                        int H, float scale) {
   extern __shared__ float sm[];
   const int Tp = (T + 63) & ~63;
   float* Qs = sm;                    // [QT][65]
@@ -293,11 +310,20 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
     int q = q0 + ty * RQ + i;
     if (q < T)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) out[((size_t)b * T + q) * (H * 64) + h * 64 + tx * 4 + j] = o[i][j];
+      for (int j = 0; j < 4; ++j) {
+        size_t at = ((size_t)b * T + q) * (H * 64) + h * 64 + tx * 4 + j;
+        if (out_lo) {
+          float hh = __uint_as_float(__float_as_uint(o[i][j]) & 0xffffe000u);
+          out[at] = hh;
+          out_lo[at] = o[i][j] - hh;
+        } else {
+          out[at] = o[i][j];
+        }
+      }
   }
 }
 
-static void attention(ts_engine* e, const float* qkv, float* out, int B, int T, int H, cudaStream_t s) {
+static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
   const int Tp = (T + 63) & ~63;
   auto smem = [&](int QT) { return (size_t)(QT * 65 + 64 * 65 + QT * Tp) * sizeof(float); };
@@ -305,13 +331,13 @@ static void attention(ts_engine* e, const float* qkv, float* out, int B, int T, 
   const size_t lim = 220 * 1024;
   if (smem(64) <= lim) {
     TS_CUDA(cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(64)));
-    attention_kernel<64><<<dim3(cdiv(T, 64), B * H), 256, smem(64), s>>>(qkv, out, T, H, scale);
+    attention_kernel<64><<<dim3(cdiv(T, 64), B * H), 256, smem(64), s>>>(qkv, out, out_lo, T, H, scale);
   } else if (smem(32) <= lim) {
     TS_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(32)));
-    attention_kernel<32><<<dim3(cdiv(T, 32), B * H), 256, smem(32), s>>>(qkv, out, T, H, scale);
+    attention_kernel<32><<<dim3(cdiv(T, 32), B * H), 256, smem(32), s>>>(qkv, out, out_lo, T, H, scale);
   } else if (smem(16) <= lim) {
     TS_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem(16)));
-    attention_kernel<16><<<dim3(cdiv(T, 16), B * H), 256, smem(16), s>>>(qkv, out, T, H, scale);
+    attention_kernel<16><<<dim3(cdiv(T, 16), B * H), 256, smem(16), s>>>(qkv, out, out_lo, T, H, scale);
   } else {
     fail(TS_ERR_UNSUPPORTED, "attention: %d frames exceed the shared-memory score tile (max ~3000 frames = 100 s)", T);
   }
@@ -319,16 +345,10 @@ static void attention(ts_engine* e, const float* qkv, float* out, int B, int T, 
   TS_CUDA(cudaGetLastError());
 }
 
-// plain GEMM on channel-last activations: y[:, coff:coff+N] = act(x W^T + b (+ res))
+// Linear on channel-last activations: y[:, coff:coff+N] = act(x W^T + b (+ res)) — a 1-tap conv
 static void linear(ts_engine* e, const Layer& L, const Act3& x, const Act3& y, int act, const Act3* res, cudaStream_t s, int coff = 0) {
   if (L.K != x.C) fail(TS_ERR_INVALID, "linear: K %d vs C %d", L.K, x.C);
-  GemmP p;
-  p.A = x.row(0, 0); p.W = L.W; p.bias = L.bias; p.C = y.row(0, 0) + coff;
-  p.M = x.B * x.T; p.N = L.N; p.K = L.K; p.mper = x.T;
-  p.a_bs = x.bstride(); p.a_rs = x.C; p.kc = L.K; p.a_ts = L.K;
-  p.c_bs = y.bstride(); p.c_rs = y.C; p.act = act; p.ldw = L.K;
-  if (res) { p.R = res->row(0, 0); p.r_bs = res->bstride(); p.r_rs = res->C; }
-  launch_gemm(e, p, s);
+  conv_auto(e, L, x, 1, 1, 0, y, x.T, act, res, s, 1, 0, coff);
 }
 
 static void face_run(ts_engine* e, const float* wave, const float* idv, float* out, int B, int N, int frame, cudaStream_t s) {
@@ -336,18 +356,19 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   // ---- wav2vec2 feature extractor ---------------------------------------------------------
   int T = (N - 10) / 5 + 1;
   double* stats = e->ws.alloc<double>((size_t)B * 512 * 2);
-  Act3 h = new_act(e, B, T, 512, 0, s);
+  const bool tc = e->use_tc;
+  Act3 h = new_act(e, B, T, 512, 0, s, tc, T & 1);     // rows per batch even for the stride-2 convs
   if (!e->ws.sizing) {
     TS_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 512 * 2 * sizeof(double), s));
     conv0_stats_kernel<<<dim3(cdiv(T, 256), B), 256, 0, s>>>(wave, F.conv0_w, N, T, stats);
-    conv0_apply_kernel<<<dim3(cdiv(T, 64), B), 256, 0, s>>>(wave, F.conv0_w, stats, F.gn_g, F.gn_b, N, T, h.p);
+    conv0_apply_kernel<<<dim3(cdiv(T, 64), B), 256, 0, s>>>(wave, F.conv0_w, stats, F.gn_g, F.gn_b, N, T, h);
     e->launches += 2;
     TS_CUDA(cudaGetLastError());
   }
   for (int i = 1; i < 7; ++i) {
     int To = (T - W2V_K[i]) / W2V_S[i] + 1;
-    Act3 y = new_act(e, B, To, 512, 0, s);
-    conv1d(e, F.conv[i], h, W2V_K[i], W2V_S[i], 0, y, To, ACT_GELU, nullptr, s);
+    Act3 y = new_act(e, B, To, 512, 0, s, tc && i < 6, To & 1);   // conv6 output feeds the interpolation: plain
+    conv_auto(e, F.conv[i], h, W2V_K[i], W2V_S[i], 0, y, To, ACT_GELU, nullptr, s);
     h = y;
     T = To;
   }
@@ -359,9 +380,10 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
     e->launches++;
     TS_CUDA(cudaGetLastError());
   }
-  ln_pre(e, hi, nullptr, F.fp_ln_g, F.fp_ln_b, hi, nullptr, ACT_NONE, s);
-  Act3 x = new_act(e, B, frame, 768, 64, s);            // padded for the k=128 positional conv
-  linear(e, F.fproj, hi, x, ACT_NONE, nullptr, s);
+  Act3 hn = new_act(e, B, frame, 512, 0, s, tc);
+  ln_pre(e, hi, nullptr, F.fp_ln_g, F.fp_ln_b, hn, nullptr, ACT_NONE, s);
+  Act3 x = new_act(e, B, frame, 768, 64, s);            // padded for the k=128 positional conv (FFMA kernel: plain)
+  linear(e, F.fproj, hn, x, ACT_NONE, nullptr, s);
   // ---- positional conv embedding (k=128, groups=16, pad 64, last output dropped) + LN -----------
   Act3 pc = new_act(e, B, frame, 768, 0, s);
   {
@@ -373,16 +395,16 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
     p.groups = 16; p.a_goff = 48; p.w_goff = (long)48 * 128 * 48; p.n_goff = 48;
     launch_gemm(e, p, s);
   }
-  Act3 hcur = new_act(e, B, frame, 768, 0, s);
+  Act3 hcur = new_act(e, B, frame, 768, 0, s, tc);
   ln_pre(e, x, &pc, F.enc_ln_g, F.enc_ln_b, hcur, nullptr, ACT_NONE, s);
   // ---- 12 post-LN transformer layers ------------------------------------------------------------
   Act3 qkv = new_act(e, B, frame, 2304, 0, s);
-  Act3 att = new_act(e, B, frame, 768, 0, s);
+  Act3 att = new_act(e, B, frame, 768, 0, s, tc);
   Act3 t1 = new_act(e, B, frame, 768, 0, s);
-  Act3 ff = new_act(e, B, frame, 3072, 0, s);
+  Act3 ff = new_act(e, B, frame, 3072, 0, s, tc);
   for (auto& L : F.layers) {
     linear(e, L.qkv, hcur, qkv, ACT_NONE, nullptr, s);
-    attention(e, qkv.p, att.p, B, frame, 12, s);
+    attention(e, qkv.p, att.p, att.lo, B, frame, 12, s);
     linear(e, L.out, att, t1, ACT_NONE, &hcur, s);                       // h + out_proj(attn)
     ln_pre(e, t1, nullptr, L.ln1_g, L.ln1_b, hcur, nullptr, ACT_NONE, s);
     linear(e, L.ff1, hcur, ff, ACT_GELU, nullptr, s);
@@ -461,7 +483,7 @@ extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
       std::copy(b, b + 768, Bv.begin() + j * 768);
     }
     L.qkv.N = 2304; L.qkv.K = 768; L.qkv.taps = 1; L.qkv.cin = 768;
-    L.qkv.W = e->upload(W);
+    upload_weights(e, W, &L.qkv);
     L.qkv.bias = e->upload(Bv);
     L.out = pack_linear(e, ck.f32(p + "attention.out_proj.weight", {768, 768}), ck.f32(p + "attention.out_proj.bias", {768}), 768, 768);
     L.ln1_g = up(e, ck.f32(p + "layer_norm.weight", {768}), 768);

@@ -28,13 +28,16 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
   const bool dense = (p.a_ts == p.kc);
 
   const float* a_ptr[LA];
+  const float* al_ptr[LA];
   const float* w_ptr[LB];
+  const float* A_lo = p.A_lo ? p.A_lo + g * p.a_goff : nullptr;
 #pragma unroll
   for (int i = 0; i < LA; ++i) {
     int row = (tid + i * NT) >> 2;
     int m = min(m0 + row, p.M - 1);
     int b = m / p.mper, t = m - b * p.mper;
     a_ptr[i] = A + b * p.a_bs + t * p.a_rs;
+    al_ptr[i] = A_lo ? A_lo + b * p.a_bs + t * p.a_rs : nullptr;
   }
 #pragma unroll
   for (int i = 0; i < LB; ++i) {
@@ -50,6 +53,10 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
       if (k < p.K) {
         int off = dense ? k : (k / p.kc) * p.a_ts + (k % p.kc);
         ra[i] = *reinterpret_cast<const float4*>(a_ptr[i] + off);
+        if (A_lo) {  // split activation (hi, lo): x = hi + lo exactly
+          float4 l = *reinterpret_cast<const float4*>(al_ptr[i] + off);
+          ra[i].x += l.x; ra[i].y += l.y; ra[i].z += l.z; ra[i].w += l.w;
+        }
       } else {
         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -117,7 +124,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
 
   const float* bias = p.bias ? p.bias + g * p.n_goff : nullptr;
   float* C = p.C + g * p.n_goff;
+  float* C_lo = p.C_lo ? p.C_lo + g * p.n_goff : nullptr;
   const float* R = p.R ? p.R + g * p.n_goff : nullptr;
+  const float* R_lo = p.R_lo ? p.R_lo + g * p.n_goff : nullptr;
   const bool vec = ((p.c_rs | p.c_bs | p.r_rs | p.r_bs | p.n_goff) & 3) == 0 && (p.N & 3) == 0 &&
                    ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && (!R || (reinterpret_cast<uintptr_t>(R) & 15) == 0);
 #pragma unroll
@@ -126,7 +135,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
     if (m >= p.M) continue;
     int b = m / p.mper, t = m - b * p.mper;
     float* crow = C + b * p.c_bs + t * p.c_rs;
+    float* crow_lo = C_lo ? C_lo + b * p.c_bs + t * p.c_rs : nullptr;
     const float* rrow = R ? R + b * p.r_bs + t * p.r_rs : nullptr;
+    const float* rrow_lo = R_lo ? R_lo + b * p.r_bs + t * p.r_rs : nullptr;
 #pragma unroll
     for (int j = 0; j < TN; j += 4) {
       int n = n0 + tx * TN + j;
@@ -138,12 +149,20 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
         float x = acc[i][j + q];
         if (nn < p.N) {
           if (bias) x += bias[nn];
-          if (rrow) x += rrow[nn];
+          if (rrow) x += rrow_lo ? (rrow[nn] + rrow_lo[nn]) : rrow[nn];
           x = act_apply(x, p.act);
         }
         v[q] = x;
       }
-      if (vec) {
+      if (crow_lo) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (n + q < p.N) {
+            float h = __uint_as_float(__float_as_uint(v[q]) & 0xffffe000u);
+            crow[n + q] = h;
+            crow_lo[n + q] = v[q] - h;
+          }
+      } else if (vec) {
         *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
       } else {
 #pragma unroll
@@ -173,14 +192,16 @@ void launch_gemm(ts_engine* e, const GemmP& p, cudaStream_t s) {
 }
 
 void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act,
-            const Act3* res, cudaStream_t s, int y_tmul, int y_toff, int x_toff) {
+            const Act3* res, cudaStream_t s, int y_tmul, int y_toff, int x_toff, int coff) {
   if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "conv1d: layer (taps %d, cin %d) vs input (k %d, C %d)", L.taps, L.cin, k, x.C);
   if (x.pad < pd) fail(TS_ERR_INVALID, "conv1d: input pad %d < conv pad %d", x.pad, pd);
   GemmP p;
   p.A = x.row(0, 0) + (long)(x_toff - pd) * x.C;
+  if (x.lo) p.A_lo = x.row_lo(0, 0) + (long)(x_toff - pd) * x.C;
+  if (y.lo) p.C_lo = y.row_lo(0, y_toff) + coff;
   p.W = L.W;
   p.bias = L.bias;
-  p.C = y.row(0, y_toff);
+  p.C = y.row(0, y_toff) + coff;
   p.M = x.B * T_out;
   p.N = L.N;
   p.K = L.K;
@@ -195,6 +216,7 @@ void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int 
   p.ldw = L.K;
   if (res) {
     p.R = res->row(0, 0);
+    if (res->lo) p.R_lo = res->row_lo(0, 0);
     p.r_bs = res->bstride();
     p.r_rs = res->C;
   }
@@ -257,6 +279,7 @@ __global__ void zero_pads_kernel(Act3 a) {
     int row = r / a.C, c = r % a.C;
     int t = row < a.pad ? row - a.pad : a.T + (row - a.pad);
     a.row(b, t)[c] = 0.f;
+    if (a.lo) a.row_lo(b, t)[c] = 0.f;
   }
 }
 

@@ -22,6 +22,12 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// The tensor core's fp32 accumulator truncates (measured: error grows linearly with K, biased toward
+// zero), so K is accumulated in TMEM only over chunks of TC_CHUNK k-blocks (K = 256); the epilogue
+// warps drain each chunk into fp32 registers (round-to-nearest adds) while the MMA warp fills the
+// other of the two TMEM accumulator buffers.
+constexpr int TC_CHUNK = 8;
+constexpr int TC_PREFETCH = 8;   // k-blocks of L2 prefetch distance for the A operand
 constexpr int TC_THREADS = 192;                             // warp0 TMA, warp1 MMA, warps 2-5 epilogue
 
 struct TcArgs {
@@ -55,6 +61,11 @@ __device__ __forceinline__ void tma_3d(void* dst, const CUtensorMap* m, int c0, 
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(s_u32(dst)),
                "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar))
                : "memory");
+}
+// TMA prefetch of a box into L2 (no shared-memory destination): hides HBM latency of k-blocks that
+// do not fit in the 3-stage ring yet
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(m), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s_u32(dst)),
@@ -104,23 +115,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* empty = full + TC_STAGES;
-  uint64_t* tmem_full = empty + TC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + TC_STAGES;   // [2] accumulator buffer ready
+  uint64_t* tempty = tfull + 2;          // [2] accumulator buffer drained (4 epilogue warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+  // N tiles vary fastest: the CTAs that share an A row block run together and hit it in L2
+  const int j0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int nk = P.taps * P.cblocks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
-    mb_init(tmem_full, 1);
+    mb_init(&tfull[0], 1); mb_init(&tfull[1], 1);
+    mb_init(&tempty[0], 4); mb_init(&tempty[1], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_lo) : "memory");
   }
-  if (warp == 1) {  // TMEM allocation: 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(TC_BN) : "memory");
+  if (warp == 1) {  // TMEM allocation: two 128-column fp32 accumulator buffers
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(2 * TC_BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -139,6 +153,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
         const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
         tma_3d(base, &mA_hi, c0, c1, c2, &full[st]);
         tma_3d(base + TC_TILE_BYTES, &mA_lo, c0, c1, c2, &full[st]);
+        if (kb + TC_PREFETCH < nk) {   // pull a later A box towards L2
+          const int kp = kb + TC_PREFETCH, tp = kp / P.cblocks, cp = kp - tp * P.cblocks;
+          tma_prefetch_3d(&mA_hi, cp * TC_BK, tp % P.stride, j0 + tp / P.stride);
+          tma_prefetch_3d(&mA_lo, cp * TC_BK, tp % P.stride, j0 + tp / P.stride);
+        }
         const int kcol = tap * P.C + cb * TC_BK;
         tma_2d(base + 2 * TC_TILE_BYTES, &mB_hi, kcol, n0, &full[st]);
         tma_2d(base + 3 * TC_TILE_BYTES, &mB_lo, kcol, n0, &full[st]);
@@ -150,20 +169,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
+        const int chunk = kb / TC_CHUNK, kin = kb - chunk * TC_CHUNK, buf = chunk & 1;
+        if (kin == 0) {                       // this accumulator buffer must have been drained
+          mb_wait(&tempty[buf], ((chunk >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         mb_wait(&full[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = s_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES,
                        b_lo = a_hi + 3 * TC_TILE_BYTES;
+        const uint32_t d = tmem_base + buf * TC_BN;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           const uint32_t o = k * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom
-          umma_tf32(tmem_base, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kb | k) != 0);
-          umma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
-          umma_tf32(tmem_base, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          umma_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+          umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+          umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
         }
         umma_commit(&empty[st]);   // stage reusable once these MMAs have read it
+        if (kin == TC_CHUNK - 1 || kb == nk - 1) umma_commit(&tfull[buf]);   // chunk accumulated
       }
-      umma_commit(tmem_full);      // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
@@ -181,17 +206,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
       t = tin / P.stride;
       valid = valid && t < P.T_out;
     }
-    mb_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // drain the K chunks into fp32 registers
+    float acc[TC_BN];
+#pragma unroll
+    for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
+    const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mb_wait(&tfull[buf], (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < TC_BN / 32; ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + cc * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += __uint_as_float(v[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tempty[buf])) : "memory");
+    }
     float* crow_hi = P.c_hi + (long)b * P.c_bs + (long)t * P.c_rs;
     float* crow_lo = P.c_lo ? P.c_lo + (long)b * P.c_bs + (long)t * P.c_rs : nullptr;
     const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
     const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
-#pragma unroll 1
+#pragma unroll
     for (int cc = 0; cc < TC_BN / 32; ++cc) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + cc * 32, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
@@ -200,7 +241,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
           float o[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            float x = __uint_as_float(v[q + u]);
+            float x = acc[cc * 32 + q + u];
             if (n + u < P.N) {
               if (P.bias) x += P.bias[n + u];
               if (rrow_hi) x += rrow_lo ? (rrow_hi[n + u] + rrow_lo[n + u]) : rrow_hi[n + u];
@@ -239,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
   }
 }
 
@@ -298,17 +339,16 @@ static CUtensorMap make_map(const float* base, int rank, const cuuint64_t* dims,
 }
 
 bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd) {
-  if (!L.W_hi || !x.lo) return false;
+  if (!L.W_hi || !x.split) return false;
   if (x.C % TC_BK) return false;
   const int rows_in = x.T + 2 * x.pad + x.tail;
   if (rows_in % stride || (x.pad - pd) % stride || x.pad < pd) return false;
-  if ((reinterpret_cast<uintptr_t>(x.p) & 15) || ((long)x.C * 4 * stride) % 16) return false;
   return true;
 }
 
 // y(b, t*y_tmul + y_toff, :) = act( conv(x)(b,t,:) + bias + res(b,t,:) );  x and W must be split (hi/lo)
 void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
-               cudaStream_t s, int y_tmul, int y_toff) {
+               cudaStream_t s, int y_tmul, int y_toff, int coff) {
   if (e->ws.sizing) return;
   if (!tc_conv_supported(L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
   if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "tc_conv1d: layer/input mismatch");
@@ -328,24 +368,44 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   TcArgs P;
   P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
   P.rows_in = rows_in; P.off = x.pad - pd; P.T_out = T_out; P.nbatch = x.B; P.Rs = (int)Rs; P.N = L.N;
-  P.c_hi = y.row(0, y_toff); P.c_lo = y.lo ? y.lo + (y.row(0, y_toff) - y.p) : nullptr;
+  P.c_hi = y.row(0, y_toff) + coff; P.c_lo = y.lo ? y.row_lo(0, y_toff) + coff : nullptr;
   P.c_bs = y.bstride(); P.c_rs = (long)y_tmul * y.C;
   P.bias = L.bias;
   P.r_hi = res ? res->row(0, 0) : nullptr;
-  P.r_lo = (res && res->lo) ? res->lo + (res->row(0, 0) - res->p) : nullptr;
+  P.r_lo = (res && res->lo) ? res->row_lo(0, 0) : nullptr;
   P.r_bs = res ? res->bstride() : 0; P.r_rs = res ? res->C : 0;
   P.act = act;
   static bool attr = false;
   if (!attr) { TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
-  dim3 grid((unsigned)((Rs + TC_BM - 1) / TC_BM), (unsigned)((L.N + TC_BN - 1) / TC_BN));
+  dim3 grid((unsigned)((L.N + TC_BN - 1) / TC_BN), (unsigned)((Rs + TC_BM - 1) / TC_BM));
   tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mAh, mAl, mBh, mBl, P);
   e->launches++;
   TS_CUDA(cudaGetLastError());
 }
 
+void upload_weights(ts_engine* e, const std::vector<float>& W, Layer* L) {
+  L->W = e->upload(W);
+  std::vector<float> hi, lo;
+  split_host(W, &hi, &lo);
+  L->W_hi = e->upload(hi);
+  L->W_lo = e->upload(lo);
+}
+
+void conv_auto(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
+               cudaStream_t s, int y_tmul, int y_toff, int coff) {
+  if (e->use_tc && (y.C % 4) == 0 && (coff % 4) == 0 && tc_conv_supported(L, x, stride, pd)) tc_conv1d(e, L, x, k, stride, pd, y, T_out, act, res, s, y_tmul, y_toff, coff);
+  else conv1d(e, L, x, k, stride, pd, y, T_out, act, res, s, y_tmul, y_toff, 0, coff);
+}
+
 }  // namespace ts
 
 using namespace ts;
+
+extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
+  if (!e) return TS_ERR_INVALID;
+  e->use_tc = enable != 0;
+  return TS_OK;
+}
 
 // debug entry: dense C[M,N] = act(A[M,K] W[N,K]^T + bias), mode 0 = FFMA kernel, 1 = tcgen05 3xTF32
 extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
@@ -367,9 +427,9 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     split_hi_lo(e, W, wh, wl, (long)N * K, s);
     Layer L;
     L.N = N; L.K = K; L.taps = 1; L.cin = K; L.W_hi = wh; L.W_lo = wl; L.bias = const_cast<float*>(bias);
-    Act3 x; x.p = ah; x.lo = al; x.B = 1; x.T = M; x.C = K; x.pad = 0;
+    Act3 x; x.p = ah; x.lo = al; x.split = true; x.B = 1; x.T = M; x.C = K; x.pad = 0;
     Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
-    tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0);
+    tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
     TS_CUDA(cudaStreamSynchronize(s));
     cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
   }

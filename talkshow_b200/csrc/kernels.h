@@ -11,9 +11,14 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_GELU = 3 };
 struct Act3 {
   float* p = nullptr;
   int B = 0, T = 0, C = 0, pad = 0;
-  __host__ __device__ long bstride() const { return (long)(T + 2 * pad) * C; }
-  __host__ __device__ float* row(int b, int t) const { return p + ((long)b * (T + 2 * pad) + pad + t) * C; }
-  __host__ __device__ size_t numel() const { return (size_t)B * (T + 2 * pad) * C; }
+  int tail = 0;          // extra (unused) rows after the back padding so rows-per-batch is a multiple of a stride
+  bool split = false;    // stored as (hi, lo) pair, see lo
+  float* lo = nullptr;   // when set the activation is stored split for the 3xTF32 tensor-core GEMM:
+                         // p = hi part (low 13 mantissa bits clear), lo = x - hi, x == p + lo exactly
+  __host__ __device__ long bstride() const { return (long)(T + 2 * pad + tail) * C; }
+  __host__ __device__ float* row(int b, int t) const { return p + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
+  __host__ __device__ float* row_lo(int b, int t) const { return lo + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
+  __host__ __device__ size_t numel() const { return (size_t)B * (T + 2 * pad + tail) * C; }
 };
 
 // C[m][n] = act( sum_k A(m,k) * W[n][k] + bias[n] + R(m,n) ), fp32 FFMA, fp32 accumulate.
@@ -26,6 +31,9 @@ struct GemmP {
   const float* bias = nullptr;
   const float* R = nullptr;
   float* C = nullptr;
+  const float* A_lo = nullptr;  // optional split operands / outputs (x = hi + lo), same indexing as A / R / C
+  const float* R_lo = nullptr;
+  float* C_lo = nullptr;
   int M = 0, N = 0, K = 0, mper = 1;
   long a_bs = 0, a_rs = 0;
   int kc = 0, a_ts = 0;
@@ -42,7 +50,7 @@ void launch_gemm(ts_engine* e, const GemmP& p, cudaStream_t s);
 // conv can interleave its even/odd phases.  res (optional) is added before the activation and is
 // indexed like y with y_tmul/y_toff = 1/0.
 void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int p, const Act3& y, int T_out,
-            int act, const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int x_toff = 0);
+            int act, const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int x_toff = 0, int coff = 0);
 
 // [B,C,T] -> padded channel-last Act3 (pads and channel padding zeroed); and back.
 void nct_to_act(ts_engine* e, const float* in, int C, const Act3& out, cudaStream_t s);
@@ -59,6 +67,18 @@ void vq_argmin(ts_engine* e, const float* codebook, const float* ee, int ncodes,
 // row-wise LayerNorm over C, y = LN(x)*g+b (+res) then act; x,y,res channel-last with C channels
 void layernorm(ts_engine* e, const Act3& x, const float* g, const float* b, const Act3& y, const Act3* res, int act,
                float eps, cudaStream_t s);
+
+// ---- tensor-core path (gemm_tc.cu): tcgen05 kind::tf32, 3xTF32 split, TMA-staged operands ------
+bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd);
+void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act,
+               const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int coff = 0);
+void split_hi_lo(ts_engine* e, const float* x, float* hi, float* lo, long n, cudaStream_t s);
+void split_host(const std::vector<float>& w, std::vector<float>* hi, std::vector<float>* lo);
+// upload W and its (hi, lo) split copies into a Layer
+void upload_weights(ts_engine* e, const std::vector<float>& W, Layer* L);
+// conv through the tensor-core kernel when the geometry allows (and e->use_tc), else the FFMA kernel
+void conv_auto(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act,
+               const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int coff = 0);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int pad4(int c) { return (c + 3) & ~3; }

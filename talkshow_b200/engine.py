@@ -72,6 +72,9 @@ class Engine:
     def pixelcnn_last_ms(self):
         return float(self.L.ts_pixelcnn_last_ms(self.h))
 
+    def set_tensor_cores(self, enable=True):
+        self._check(self.L.ts_set_tensor_cores(self.h, int(enable)), "ts_set_tensor_cores")
+
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
 

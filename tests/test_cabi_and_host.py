@@ -1,0 +1,139 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every symbol include/talkshow_b200.h
+declares (no compute calls), host-side mirrors of the reference interface behave like the
+reference (config schema, flags, pose layout, sharding, noise contract, error conventions)."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import talkshow_oracle as O
+from conftest import ROOT
+from talkshow_b200 import _lib, synth
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "talkshow_b200.h")).read()
+    names = set(re.findall(r"\b(ts_[a-z0-9_]+)\s*\(", hdr))
+    names -= {"ts_engine", "ts_tensor", "ts_status"}
+    assert len(names) >= 24
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), "libtalkshow_b200.so does not export %s" % n
+    # and the ctypes binding covers all of them
+    assert names <= set(_lib.SYMBOLS), names - set(_lib.SYMBOLS)
+
+
+def test_error_convention_without_gpu():
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    if torch.cuda.is_available():
+        pytest.skip("checks the no-device error path")
+    rc = L.ts_engine_create(ctypes.byref(h), 0)
+    assert rc != 0 and not h.value
+    assert len(L.ts_last_error(None)) > 0
+    assert L.ts_latent_rows(300) == 75 and L.ts_latent_rows(120) == 30 and L.ts_latent_rows(88) == 22
+
+
+def test_host_only_engine_rejects_execution_and_bad_checkpoints():
+    from talkshow_b200.engine import Engine
+
+    e = Engine(-148)
+    sd = synth.pixelcnn_state(0)
+    bad = dict(sd)
+    bad.pop("layers.3.horiz_resid.bias")
+    with pytest.raises(RuntimeError, match="horiz_resid.bias"):
+        e.load_pixelcnn(bad)
+    bad = dict(sd)
+    bad["fusion_v.weight"] = torch.zeros(256, 256, 1, 1)
+    with pytest.raises(RuntimeError, match="fusion_v.weight"):
+        e.load_pixelcnn(bad)
+    e.load_pixelcnn(sd)
+    assert e.pixelcnn_row_bytes == 89774080
+    assert e.pixelcnn_staged_row_bytes > e.pixelcnn_row_bytes
+    e.close()
+
+
+def test_wrappers_refuse_cpu_device():
+    """No CPU fallback: the reference accepts args.gpu='cpu', the product must fail loudly."""
+    from talkshow_b200.nets import s2g_body_pixel
+    from talkshow_b200.trainer.config import load_JsonConfig
+
+    cfg = load_JsonConfig(os.path.join(ROOT, "config", "body_pixel.json"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        s2g_body_pixel(types.SimpleNamespace(gpu="cpu", infer=True), cfg)
+
+
+def test_config_schema_matches_reference_fields():
+    from talkshow_b200.trainer.config import load_JsonConfig
+
+    for name in ("body_pixel", "body_vq", "face"):
+        c = load_JsonConfig(os.path.join(ROOT, "config", name + ".json"))
+        assert c.Data.pose.convert_to_6d is False and c.Data.pose.expression is True
+        assert c.Data.pose.generate_length == 88 and c.Data.pose.normalization is False
+        assert isinstance(c.Model.model_name, str) and isinstance(c.Log.name, str)
+        assert c.Train.learning_rate.generator_learning_rate == 1e-4
+    c = load_JsonConfig(os.path.join(ROOT, "config", "body_pixel.json"))
+    assert c.Model.code_num == 2048 and c.Model.bh_model and c.Model.composition and c.Model.vq_path
+
+
+def test_cli_flags():
+    from talkshow_b200.trainer.options import parse_args
+
+    a = parse_args(["--config_file", "./config/body_pixel.json", "--infer", "--audio_file", "x.wav", "--id", "2",
+                    "--num_sample", "12", "--body_model_name", "s2g_body_pixel"])
+    assert a.infer and a.id == 2 and a.num_sample == 12 and a.gpu == 0 and a.audio_file == "x.wav"
+
+
+def test_pose_layout_helpers():
+    from talkshow_b200.data_utils.lower_body import c_index_3d, part2full
+
+    assert len(c_index_3d) == 129 and list(c_index_3d) == O.C_INDEX_3D
+    x = torch.arange(3 * 232, dtype=torch.float32).view(3, 232)
+    assert torch.equal(part2full(x), O.part2full(x))
+    assert torch.equal(part2full(x, stand=True), O.part2full(x, stand=True))
+    assert part2full(x).shape == (3, 265)
+
+
+def test_shard_ranges_cover_batch():
+    from talkshow_b200.pipeline import shard_range
+
+    for B, G in ((12, 8), (64, 8), (12, 1), (5, 4), (64, 2)):
+        r = [shard_range(B, k, G) for k in range(G)]
+        assert r[0][0] == 0 and r[-1][1] == B
+        assert all(r[i][1] == r[i + 1][0] for i in range(G - 1))
+        assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
+    assert [hi - lo for lo, hi in (shard_range(12, k, 8) for k in range(8))] == [2, 2, 2, 2, 1, 1, 1, 1]
+
+
+def test_noise_contract_matches_reference_multinomial():
+    """draw_sampler_noise(per_step=True) consumes the generator exactly like the reference's
+    probs.multinomial(1) calls: argmax(p/q) with our q == multinomial under the same seed."""
+    from talkshow_b200.nets.base import draw_sampler_noise
+
+    B, T = 3, 4
+    probs = torch.softmax(torch.randn(2 * T, B, 2048, generator=torch.Generator().manual_seed(1)) * 3, -1)
+    torch.manual_seed(77)
+    ref = torch.stack([probs[s].multinomial(1).squeeze(-1) for s in range(2 * T)])
+    torch.manual_seed(77)
+    q = draw_sampler_noise(T, B, "cpu", per_step=True)
+    assert torch.equal(torch.argmax(probs / q, -1), ref)
+
+
+def test_mfcc_front_end_shapes(tmp_path):
+    from scipy.io import wavfile
+
+    from talkshow_b200.data_utils.utils import get_mfcc_ta
+
+    sr = 16000
+    x = (synth.synth_wave(1, sr * 4)[0].numpy() * 20000).astype(np.int16)
+    p = str(tmp_path / "a.wav")
+    wavfile.write(p, sr, np.stack([x, x], 1))          # stereo int16
+    m = get_mfcc_ta(p, sr=22000, fps=30, smlpx=True, type="mfcc")
+    assert m.shape == (120, 64) and np.isfinite(m).all()            # M = 4 s * 30 fps, SURVEY.md §8
+    w = get_mfcc_ta(p, am=True, am_sr=16000, fps=30, encoder_choice="faceformer")
+    assert w.shape == (sr * 4, 1)
+    assert O.latent_rows(120) == 30
