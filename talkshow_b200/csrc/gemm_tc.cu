@@ -18,9 +18,14 @@
 
 namespace ts {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
-constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;            // 16 KB per operand tile
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
+// 128 x 256 CTA tile: with N = 256 one UMMA reads 4 KB of A + 8 KB of B from shared memory per 128
+// tensor clocks (96 B/clk) instead of 8 KB per 64 clocks at N = 128 (128 B/clk = the whole smem port),
+// which measured as the limiter of the 128 x 128 version (multicast and L2 prefetch changed nothing).
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 32, TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;               // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;               // 32 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;   // A_hi, A_lo, B_hi, B_lo = 96 KB
+constexpr int TC_EPI_WARPS = 8;                             // 4 TMEM lane quadrants x 2 column halves
 constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 // The tensor core's fp32 accumulator truncates (measured: error grows linearly with K, biased toward
 // zero), so K is accumulated in TMEM only over chunks of TC_CHUNK k-blocks (K = 256); the epilogue
@@ -28,7 +33,7 @@ constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barr
 // other of the two TMEM accumulator buffers.
 constexpr int TC_CHUNK = 8;
 constexpr int TC_PREFETCH = 8;   // k-blocks of L2 prefetch distance for the A operand
-constexpr int TC_THREADS = 192;                             // warp0 TMA, warp1 MMA, warps 2-5 epilogue
+constexpr int TC_THREADS = 128 + 32 * TC_EPI_WARPS;          // warpgroup 0: TMA, MMA (+2 idle); warps 4-19 epilogue
 
 struct TcArgs {
   int taps, cblocks, stride;        // K loop = taps x (C / 32)
@@ -44,6 +49,8 @@ struct TcArgs {
   const float* r_lo;
   long r_bs, r_rs;
   int act;
+  int nprod;                        // 3 (normal) or 1 (hi*hi only: throughput experiment)
+  int cn, cm;                       // cluster shape: cn N-tiles x cm M-tiles share operands by TMA multicast
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +78,34 @@ __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* m, int c0, 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(s_u32(dst)),
                "l"(m), "r"(c0), "r"(c1), "r"(s_u32(bar))
                : "memory");
+}
+// multicast variants: the box lands at the same smem offset in every CTA of `mask` and completes tx
+// bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_3d_mc(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
+          s_u32(dst)),
+      "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(s_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_2d_mc(void* dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          s_u32(dst)),
+      "l"(m), "r"(c0), "r"(c1), "r"(s_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 // K-major, 128B-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (=1), version 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -101,6 +136,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
 __device__ __forceinline__ float tc_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == ACT_LRELU) return v > 0.f ? v : 0.2f * v;
@@ -122,25 +165,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
   // N tiles vary fastest: the CTAs that share an A row block run together and hit it in L2
   const int j0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
   const int nk = P.taps * P.cblocks;
+  // cluster = cn x cm tiles; CTAs in my row (same M tile) share the A box, CTAs in my column share the B box
+  const uint32_t crank = cluster_ctarank();
+  const int cx = crank % P.cn, cy = crank / P.cn;
+  const uint16_t mask_row = (uint16_t)(((1u << P.cn) - 1u) << (cy * P.cn));
+  uint16_t mask_col = 0;
+  for (int j = 0; j < P.cm; ++j) mask_col |= (uint16_t)(1u << (j * P.cn + cx));
+  const bool clustered = P.cn * P.cm > 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    // a stage is free once every CTA that received one of my slices has consumed it: cn + cm - 1 arrivals
+    for (int i = 0; i < TC_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], P.cn + P.cm - 1); }
     mb_init(&tfull[0], 1); mb_init(&tfull[1], 1);
-    mb_init(&tempty[0], 4); mb_init(&tempty[1], 4);
+    mb_init(&tempty[0], TC_EPI_WARPS); mb_init(&tempty[1], TC_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_lo) : "memory");
   }
-  if (warp == 1) {  // TMEM allocation: two 128-column fp32 accumulator buffers
+  if (warp == 1) {  // TMEM allocation: two 256-column fp32 accumulator buffers (all 512 columns)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(2 * TC_BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (clustered) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts / arrives remotely
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
@@ -150,17 +203,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
         const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
         unsigned char* base = smem + st * TC_STAGE_BYTES;
         mb_expect(&full[st], TC_STAGE_BYTES);
-        const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
-        tma_3d(base, &mA_hi, c0, c1, c2, &full[st]);
-        tma_3d(base + TC_TILE_BYTES, &mA_lo, c0, c1, c2, &full[st]);
-        if (kb + TC_PREFETCH < nk) {   // pull a later A box towards L2
-          const int kp = kb + TC_PREFETCH, tp = kp / P.cblocks, cp = kp - tp * P.cblocks;
-          tma_prefetch_3d(&mA_hi, cp * TC_BK, tp % P.stride, j0 + tp / P.stride);
-          tma_prefetch_3d(&mA_lo, cp * TC_BK, tp % P.stride, j0 + tp / P.stride);
-        }
+        // my slices: rows [cx*128/cn, +128/cn) of the A box, rows [cy*128/cm, +128/cm) of the B box
+        const int ar = TC_BM / P.cn, br = TC_BN / P.cm;
+        const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride + cx * ar;
+        tma_3d_mc(base + cx * ar * 128, &mA_hi, c0, c1, c2, &full[st], mask_row);
+        tma_3d_mc(base + TC_A_BYTES + cx * ar * 128, &mA_lo, c0, c1, c2, &full[st], mask_row);
         const int kcol = tap * P.C + cb * TC_BK;
-        tma_2d(base + 2 * TC_TILE_BYTES, &mB_hi, kcol, n0, &full[st]);
-        tma_2d(base + 3 * TC_TILE_BYTES, &mB_lo, kcol, n0, &full[st]);
+        tma_2d_mc(base + 2 * TC_A_BYTES + cy * br * 128, &mB_hi, kcol, n0 + cy * br, &full[st], mask_col);
+        tma_2d_mc(base + 2 * TC_A_BYTES + TC_B_BYTES + cy * br * 128, &mB_lo, kcol, n0 + cy * br, &full[st], mask_col);
       }
     }
   } else if (warp == 1) {
@@ -176,23 +226,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
         }
         mb_wait(&full[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = s_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES, b_hi = a_hi + 2 * TC_TILE_BYTES,
-                       b_lo = a_hi + 3 * TC_TILE_BYTES;
+        const uint32_t a_hi = s_u32(smem + st * TC_STAGE_BYTES), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES,
+                       b_lo = b_hi + TC_B_BYTES;
         const uint32_t d = tmem_base + buf * TC_BN;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           const uint32_t o = k * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom
-          umma_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
-          umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
-          umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          if (P.nprod == 3) {
+            umma_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+            umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+            umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          } else {
+            umma_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+          }
         }
-        umma_commit(&empty[st]);   // stage reusable once these MMAs have read it
+        umma_commit_mc(&empty[st], mask_row | mask_col);   // release the stage to every CTA that filled it
         if (kin == TC_CHUNK - 1 || kb == nk - 1) umma_commit(&tfull[buf]);   // chunk accumulated
       }
     }
-  } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quadrants (warp % 4) =====
+  } else if (warp >= 4) {
+    // ===== epilogue: warps 4..19; TMEM lane quadrant = warp % 4, column quarter = (warp - 4) / 4 =====
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int EC = TC_BN / (TC_EPI_WARPS / 4);     // columns per epilogue thread (128)
     const int row = quad * 32 + lane;
     const int j = j0 + row;
     // GEMM row j <-> padded input row j*stride -> (batch, output step)
@@ -207,21 +263,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
       valid = valid && t < P.T_out;
     }
     // drain the K chunks into fp32 registers
-    float acc[TC_BN];
+    float acc[EC];
 #pragma unroll
-    for (int i = 0; i < TC_BN; ++i) acc[i] = 0.f;
+    for (int i = 0; i < EC; ++i) acc[i] = 0.f;
     const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
     for (int c = 0; c < nchunks; ++c) {
       const int buf = c & 1;
       mb_wait(&tfull[buf], (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-      for (int cc = 0; cc < TC_BN / 32; ++cc) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + cc * 32, v);
+      for (int cc = 0; cc < EC / 16; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[cc * 32 + i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -232,11 +288,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
     const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
     const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
 #pragma unroll
-    for (int cc = 0; cc < TC_BN / 32; ++cc) {
+    for (int cc = 0; cc < EC / 32; ++cc) {
       if (valid) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4) {
-          const int n = n0 + cc * 32 + q;
+          const int n = n0 + half * EC + cc * 32 + q;
           if (n >= P.N) break;
           float o[4];
 #pragma unroll
@@ -278,6 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (clustered) cluster_sync_all();   // nobody exits while a peer may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
@@ -359,11 +416,18 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   const float* base_lo = x.lo;
   cuuint64_t adims[3] = {(cuuint64_t)x.C, (cuuint64_t)stride, (cuuint64_t)Rs};
   cuuint64_t astr[2] = {(cuuint64_t)x.C * 4, (cuuint64_t)x.C * 4 * stride};
-  cuuint32_t abox[3] = {TC_BK, 1, TC_BM};
+  // cluster shape: up to 4 N-tiles x 2 M-tiles share their operand boxes by TMA multicast
+  const int tiles_n = (L.N + TC_BN - 1) / TC_BN, tiles_m = (int)((Rs + TC_BM - 1) / TC_BM);
+  int cn = 1, cm = 1;
+  if (e->tc_multicast) {
+    cn = (tiles_n % 4 == 0) ? 4 : (tiles_n % 2 == 0) ? 2 : 1;
+    cm = tiles_m >= 2 ? 2 : 1;
+  }
+  cuuint32_t abox[3] = {TC_BK, 1, (cuuint32_t)(TC_BM / cn)};
   CUtensorMap mAh = make_map(base_hi, 3, adims, astr, abox), mAl = make_map(base_lo, 3, adims, astr, abox);
   cuuint64_t bdims[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
   cuuint64_t bstr[1] = {(cuuint64_t)L.K * 4};
-  cuuint32_t bbox[2] = {TC_BK, TC_BN};
+  cuuint32_t bbox[2] = {TC_BK, (cuuint32_t)(TC_BN / cm)};
   CUtensorMap mBh = make_map(L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(L.W_lo, 2, bdims, bstr, bbox);
   TcArgs P;
   P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
@@ -375,10 +439,23 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.r_lo = (res && res->lo) ? res->row_lo(0, 0) : nullptr;
   P.r_bs = res ? res->bstride() : 0; P.r_rs = res ? res->C : 0;
   P.act = act;
+  P.cn = cn; P.cm = cm;
+  { const char* np = getenv("TS_TC_NPROD"); P.nprod = (np && np[0] == '1') ? 1 : 3; }
   static bool attr = false;
   if (!attr) { TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
-  dim3 grid((unsigned)((L.N + TC_BN - 1) / TC_BN), (unsigned)((Rs + TC_BM - 1) / TC_BM));
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(mAh, mAl, mBh, mBl, P);
+  // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
+  dim3 grid((unsigned)(((tiles_n + cn - 1) / cn) * cn), (unsigned)(((tiles_m + cm - 1) / cm) * cm));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cn; at[0].val.clusterDim.y = cm; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));
   e->launches++;
   TS_CUDA(cudaGetLastError());
 }
@@ -404,6 +481,7 @@ using namespace ts;
 extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   if (!e) return TS_ERR_INVALID;
   e->use_tc = enable != 0;
+  e->tc_multicast = enable != 2;   // 2 = tensor cores without cluster multicast (A/B measurements)
   return TS_OK;
 }
 
