@@ -268,7 +268,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
     }
     P->d_cls = e->upload(cls);
     P->d_arena = (float*)e->dmalloc((size_t)P->lay.total * sizeof(float) + 256);
-    P->d_barrier = (unsigned*)e->dmalloc(256);
+    P->d_barrier = (unsigned*)e->dmalloc(4096);   // one flag word per CTA
   }
   return P;
 }
@@ -328,17 +328,16 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 }
 
 // CTA arrives at the grid barrier: all of this CTA's global writes become visible before the count moves
+// (bar.sync orders the CTA's writes before thread 0's release; red.release.gpu / ld.acquire.gpu carry the
+// inter-CTA ordering, so no separate fences are needed.  A flag-per-CTA barrier polled by a whole warp was
+// measured slower: 148 CTAs polling 5 lines is a worse L2 hot spot than one counter.)
 __device__ __forceinline__ void grid_arrive(unsigned* ctr) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    red_release_add(ctr, 1u);
-  }
+  if (threadIdx.x == 0) red_release_add(ctr, 1u);
 }
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
   if (threadIdx.x == 0) {
     while (ld_acquire(ctr) < target) { /* spin */ }
-    __threadfence();
   }
   __syncthreads();
 }
@@ -392,8 +391,11 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j) acc[j] = make_float2(0.f, 0.f);
   const int kper = K >> 3;  // K is a multiple of 256 -> 32 | kper
-  const int kbeg = warp * kper;
-  constexpr int U = 16;
+  // K slices are rotated by CTA so that the 148 CTAs do not all pull the same L2 lines at the same time;
+  // partials are stored by slice index, so the reduction order does not depend on the rotation
+  const int slice = (warp + blockIdx.x) & 7;
+  const int kbeg = slice * kper;
+  constexpr int U = 32;   // K = 256 stages issue their whole K slice in one batch of loads
   for (int k0 = kbeg; k0 < kbeg + kper; k0 += U) {
     const float* base = arena + seg[k0 >> 8] + ((k0 & 255) << 6) + lane * 2;
     float2 x[U];
@@ -414,7 +416,7 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
   }
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j)
-    *reinterpret_cast<float2*>(&red[(warp * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
 }
 
 __device__ __forceinline__ float red_sum(const float* red, int j, int m) {
@@ -426,15 +428,49 @@ __device__ __forceinline__ float red_sum(const float* red, int j, int m) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // one matmul task (all passes): weights already in Wsm
-__device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, int* s_seg) {
+struct EpiPre {  // epilogue operands fetched before the grid-barrier wait (they do not depend on the previous stage)
+  float a, b;
+  bool valid;
+};
+
+// operands of thread-item `tid` of an H-pass task whose epilogue has at most one item per thread
+__device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixArgs& A, int r) {
+  EpiPre p;
+  p.a = 0.f; p.b = 0.f; p.valid = false;
+  const int tid = threadIdx.x, m = tid & (PIX_MB - 1), j = tid >> 6;
+  const PixLayout& a = A.lay;
+  if (t.epi == EPI_HGATE) {
+    if (j < (t.nrows >> 1) && (t.nrows >> 1) * PIX_MB <= PIX_THREADS) {
+      const int q = (t.row0 >> 1) + j;
+      const float* v2h = A.arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
+      p.a = __ldcg(v2h + q * PIX_MB + m);
+      p.b = __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
+      p.valid = true;
+    }
+  } else if (t.epi == EPI_HRES && t.layer > 0) {
+    if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
+      p.a = __ldcg(A.arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + (t.row0 + j) * PIX_MB + m);
+      p.valid = true;
+    }
+  } else if (t.epi == EPI_FUSEH) {
+    if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
+      p.a = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + t.row0 + j] : 0.f;
+      p.valid = true;
+    }
+  }
+  return p;
+}
+
+__device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, const EpiPre& pre) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PixLayout& a = A.lay;
   const int npass = (t.epi == EPI_V2H || t.epi == EPI_FUSEV) ? 2 : 1;
   const float* bias = Wsm + (size_t)t.K * t.rpad;
   float* arena = A.arena;
   for (int pass = 0; pass < npass; ++pass) {
-    if (tid == 0) resolve_segments(t, pass, r, a, A.L, s_seg);
-    __syncthreads();  // s_seg visible; previous pass's epilogue finished reading red
+    int s_seg[6];
+    resolve_segments(t, pass, r, a, A.L, s_seg);
+    if (pass > 0) __syncthreads();  // previous pass's epilogue finished reading red
     if (t.K > 0) {
       switch (t.rpad >> 2) {
         case 1: mm_rows<1>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
@@ -456,8 +492,10 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
         float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
         if (t.epi == EPI_HGATE) {
           const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
-          float zt = (__ldcg(v2h + q * PIX_MB + m) + at) + ct;
-          float zs = (__ldcg(v2h + (PIX_D + q) * PIX_MB + m) + as) + cs;
+          float vt = pre.valid ? pre.a : __ldcg(v2h + q * PIX_MB + m);
+          float vs = pre.valid ? pre.b : __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
+          float zt = (vt + at) + ct;
+          float zs = (vs + as) + cs;
           arena[a.G + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
         } else {
           float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
@@ -480,12 +518,12 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
           case EPI_HRES:
             if (t.layer == 0) arena[a.XHP + ch * PIX_MB + m] = v;
             else {
-              float xh = __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
+              float xh = pre.valid ? pre.a : __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
               arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
             }
             break;
           case EPI_FUSEH: {
-            float au = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
+            float au = pre.valid ? pre.a : (m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f);
             arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
           } break;
           case EPI_OUT1: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
@@ -577,7 +615,6 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
   float* wbuf = reinterpret_cast<float*>(smem_raw);
   float* red = wbuf + 2 * PIX_WBUF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * PIX_MAXROWS * PIX_MB);
-  __shared__ int s_seg[8];
   const int tid = threadIdx.x, cta = blockIdx.x;
 
   if (!PERSISTENT) {
@@ -588,7 +625,8 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     const int nf = (t.K + 1) * t.rpad;
     for (int i = tid; i < nf; i += PIX_THREADS) wbuf[i] = A.blob[t.wofs + i];
     __syncthreads();
-    run_matmul_task(t, A, r_single, wbuf, red, s_seg);
+    EpiPre pre; pre.a = pre.b = 0.f; pre.valid = false;
+    run_matmul_task(t, A, r_single, wbuf, red, pre);
     return;
   }
 
@@ -626,11 +664,14 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     }
     const bool active = task_active(t, r, A.log_r0);
     const bool has_w = active && t.epi != EPI_SAMPLE;  // K == 0 tasks still stage their bias row
+    EpiPre pre;
+    pre.a = pre.b = 0.f; pre.valid = false;
+    if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue(t, A, r);   // in flight while we wait below
     if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
     if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);  // every CTA finished stage g-1
     if (active) {
       if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
-      else run_matmul_task(t, A, r, wbuf + buf * PIX_WBUF, red, s_seg);
+      else run_matmul_task(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
     grid_arrive(A.barrier);
     if (++s == A.nstages) { s = 0; ++r; }
@@ -704,7 +745,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   launch_gemm(e, h, s);
 
   TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)P->lay.total * sizeof(float), s));
-  TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 256, s));
+  TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 4096, s));
   build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, P->lay.CLS, P->L, P->nclasses, B);
   e->launches++;
   TS_CUDA(cudaGetLastError());
