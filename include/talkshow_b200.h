@@ -127,7 +127,8 @@ int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const 
 /* 1 (default): face / VQ-decoder contractions run on the tcgen05 3xTF32 tensor-core kernel;
  * 0: everything on the fp32 FFMA kernel (A/B comparison in tests and profiles). */
 int ts_set_tensor_cores(ts_engine* e, int enable);
-/* 0 = persistent cooperative kernel (default), 1 = one launch per stage (debug cross-check) */
+/* 0 = v1 persistent cooperative kernel (grid barrier), 1 = v1 one launch per stage (debug cross-check),
+ * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
 
 #ifdef __cplusplus

@@ -23,6 +23,14 @@ for B in (64, 8, 1):
         torch.cuda.synchronize()
     print("B=%d audio %.3f ms  pixelcnn %.3f ms (%.1f us/row)  decode %.3f ms  fused %.3f ms -> %.0f frames/s" % (
         B, t0.elapsed_time(t1), t1.elapsed_time(t2), t1.elapsed_time(t2)*1000/T, t2.elapsed_time(t3), t3.elapsed_time(t4), B*300/(t3.elapsed_time(t4)/1e3)))
+import sys
+e.set_pixelcnn_mode(2)
+for B in (64, 8):
+    mfcc = synth.synth_mfcc(B, 300).cuda(); label = (torch.arange(B) % 4).cuda(); noise = torch.empty(150, B, 2048, device='cuda').exponential_(1)
+    a = e.audio_encode(mfcc)
+    for it in range(2):
+        t1 = ev(); codes = e.pixelcnn_generate(a, label, noise); t2 = ev(); torch.cuda.synchronize()
+    print('v2 cluster mode B=%d: %.3f ms (%.1f us/row)' % (B, t1.elapsed_time(t2), t1.elapsed_time(t2)*1000/75)); sys.stdout.flush()
 e.set_pixelcnn_mode(1)
 B=64; mfcc = synth.synth_mfcc(B, 300).cuda(); label = (torch.arange(B) % 4).cuda(); noise = torch.empty(150, B, 2048, device='cuda').exponential_(1)
 a = e.audio_encode(mfcc)

@@ -678,6 +678,8 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
   }
 }
 
+#include "pixelcnn2.inc"
+
 __global__ void build_cls_kernel(const float* __restrict__ cls_w, const int64_t* __restrict__ label, float* arena, int cls_off,
                                  int L, int ncls, int B) {
   // CLS[l][ch][m] = class_cond_embedding_l[label[m]][ch]
@@ -730,6 +732,8 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   float* a_emb = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
   float* audv = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
   float* audh = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
+  const int nclusters = (B + C2_MB - 1) / C2_MB;
+  float* arena2 = (e->pixel_mode == 2 && P->p2) ? e->ws.alloc<float>((size_t)nclusters * ((Plan2*)P->p2)->lay.total) : nullptr;
   if (e->ws.sizing) return;
   GemmP g;
   g.A = aud.row(b0, 0); g.W = P->emb_aud.W; g.bias = P->emb_aud.bias; g.C = a_emb;
@@ -744,6 +748,33 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   h.W = P->fuse_h_a.W; h.bias = P->fuse_h_a.bias; h.C = audh;
   launch_gemm(e, h, s);
 
+  if (e->pixel_mode == 2) {
+    // v2: one 16-CTA cluster per 8 samples, no grid barrier (pixelcnn2.inc)
+    Plan2* Q = (Plan2*)P->p2;
+    Pix2Args A2;
+    A2.jobs = Q->d_jobs; A2.njobs = Q->d_njobs; A2.chunks = Q->d_chunks; A2.blob = Q->d_blob; A2.bias = Q->d_bias;
+    A2.arena = arena2; A2.emb = P->d_emb; A2.cls_w = P->d_cls; A2.audv = audv; A2.audh = audh; A2.noise = noise; A2.label = label;
+    A2.pre = pre; A2.idx_out = idx_out; A2.logits_out = logits_out; A2.lay = Q->lay; A2.rank_stride = Q->rank_stride;
+    A2.B = B; A2.T0 = T0; A2.Ttot = Ttot; A2.log_r0 = logits_all ? 0 : T0; A2.L = P->L; A2.nstages = Q->nstages;
+    A2.nchunks_row = Q->nchunks_row; A2.ncls = P->nclasses;
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nclusters * C2_CL);
+    cfg.blockDim = dim3(C2_THREADS);
+    cfg.dynamicSmemBytes = C2_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C2_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
+    TS_CUDA(cudaLaunchKernelEx(&cfg, pixelcnn2_kernel, A2));
+    if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
+    e->launches++;
+    return;
+  }
   TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)P->lay.total * sizeof(float), s));
   TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 4096, s));
   build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, P->lay.CLS, P->L, P->nclasses, B);
@@ -778,7 +809,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
 void pixelcnn_generate_act(ts_engine* e, const Act3& aud, const int64_t* label, const float* noise, int64_t* idx_out,
                            float* logits_out, int B, int T, const int64_t* pre, int T0, cudaStream_t s, bool logits_all) {
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
-  if (B > PIX_MB)
+  if (B > PIX_MB && e->pixel_mode != 2)
     fail(TS_ERR_UNSUPPORTED, "pixelcnn: batch tile is %d samples per call (got %d); the host shim chunks larger batches", PIX_MB, B);
   generate_chunk(e, aud, 0, label, noise, B, idx_out, logits_out, B, T, pre, T0, s, logits_all);
 }
@@ -791,6 +822,7 @@ extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
   PixelPlan* P = build_plan(e, ck);
+  P->p2 = build_plan2(e, ck, P->L);
   delete e->pix;
   e->pix = P;
   TS_API_END(e)

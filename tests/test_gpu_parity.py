@@ -85,9 +85,10 @@ def test_vq_roundtrip_output(eng, ckpts):
     assert np.abs(out - gold["out"]).max() <= TOL
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 0, 2])
 def test_pixelcnn_teacher_forced_logits(eng, ckpts, mode):
-    """mode 1 = one launch per stage (cross-check), mode 0 = persistent cooperative kernel."""
+    """mode 1 = v1 one launch per stage (cross-check), 0 = v1 persistent cooperative kernel,
+    2 = v2 cluster-per-8-samples kernel."""
     eng.set_pixelcnn_mode(mode)
     try:
         sd = ckpts["pixel"]["generator"]
@@ -105,7 +106,7 @@ def test_pixelcnn_teacher_forced_logits(eng, ckpts, mode):
         eng.set_pixelcnn_mode(0)
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 0, 2])
 def test_pixelcnn_generate_b1_t30(eng, ckpts, mode):
     """BASELINE config 3: B=1, 4 s, id=0 — bit-exact code sequence vs oracle and golden."""
     eng.set_pixelcnn_mode(mode)
