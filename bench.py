@@ -199,6 +199,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         tsbuild.build()
@@ -265,6 +267,17 @@ def run_ours(args, rank, world, local_rank):
     eng.pixelcnn_timing(False)
     pix_ms = [x for x in pix_ms if x > 0]
     pix_avg = sum(pix_ms) / len(pix_ms)
+    # dense-contraction side of the step: the face regressor alone (wav2vec2 CNN + transformer; tcgen05 3xTF32)
+    idz = torch.zeros(B, 4, device=dev)
+    face_ms = []
+    for _ in range(3):
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        eng.face_forward(wave_d, idz, F)
+        f1.record()
+        torch.cuda.synchronize()
+        face_ms.append(f0.elapsed_time(f1))
+    face_avg = sum(face_ms[1:]) / len(face_ms[1:])
 
     frames_step = B * world * F
     value = frames_step * args.steps / (dev_ms / 1e3)
@@ -281,10 +294,18 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"kernel": "pixelcnn_kernel<true> (persistent gated-PixelCNN sampler, %d rows/launch)" % T,
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": eng.pixelcnn_staged_row_bytes * T, "traffic_source": "staged blob bytes per launch; ncu "
-                "dram__bytes_read+write of the same kernel in profiles/", "launch_ms": pix_avg,
+                "traffic": eng.pixelcnn_staged_row_bytes * T, "traffic_source": "bytes the kernel stages per launch (packed "
+                "blob); ncu dram__bytes_read+write of the same kernel: 154 MB/row (profiles/r01_pixelcnn_v1_ncu_summary.md)", "launch_ms": pix_avg,
                 "algorithmic_bytes": alg_bytes, "share_of_step": pix_avg / (dev_ms / args.steps)}
 
+    # 106 GFLOP per 10 s clip (53 GMAC), scaled with the clip length
+    face_flop = 106.0e9 * B * args.seconds / 10.0
+    tf32x3_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 / 3.0     # tf32 rate = bf16/2, three products per MAC
+    roofline_dense = {"kernel": "face path (tc_gemm_kernel x56 + attention + FFMA layers per forward)", "bound": "tensor",
+                      "achieved": face_flop / (face_avg * 1e-3) / 1e12, "peak": tf32x3_peak, "unit": "TFLOP/s",
+                      "frac": face_flop / (face_avg * 1e-3) / 1e12 / tf32x3_peak,
+                      "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32) / 3 (3xTF32 split)" if peaks else "fallback 1590/6",
+                      "traffic": None, "launch_ms": face_avg, "share_of_step": face_avg / (dev_ms / args.steps)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": "frames/s",
                 "h2d_bytes_per_step": (wave_p.numel() * 4 + mfcc_p.numel() * 4 + label_p.numel() * 8) * world,
                 "d2h_bytes_per_step": out_p.numel() * 4 * world, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(l1 - l0), "clocks": clk.summary(), "roofline": roofline,
+        "gpu_launches": int(l1 - l0), "clocks": clk.summary(), "roofline": roofline, "roofline_dense": roofline_dense,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.stderr.write("[bench] device legs done: value %.0f frames/s, e2e %.0f frames/s; timing the CPU arm sample\n" % (value, e2e_val))

@@ -100,6 +100,12 @@ int ts_face_forward(ts_engine* e, const float* wave, const float* id, float* out
 int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise, int64_t* codes,
                      float* poses, int B, int M, void* stream);
 
+/* Audio front-end of get_mfcc_ta, data_utils/utils.py:148-177: wave [B,N] mono at
+ * `sr` Hz -> torchaudio Resample(sr, 22000) -> MFCC(64 coefficients, n_fft 2048, hop 734 = 30 fps, 256 HTK
+ * mels, top_db 80, DCT-II ortho) -> out [B,64,M], M = ts_mfcc_frames(N, sr). */
+int ts_mfcc(ts_engine* e, const float* wave, float* out, int B, int N, int sr, void* stream);
+int ts_mfcc_frames(int N, int sr);
+
 /* scripts/demo.py:182-229 + data_utils/lower_body.py:68-87 (part2full): face [B,Ff,103],
  * body [B,Fb,129] -> out [B,Ff,265]; body is padded with its last frame / truncated to Ff. */
 int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* out, int B, int Ff, int Fb,

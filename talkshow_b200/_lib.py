@@ -45,6 +45,8 @@ SYMBOLS = {
                                    C.c_int, C.c_void_p]),
     "ts_assemble_pose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_int, C.c_void_p]),
+    "ts_mfcc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ts_mfcc_frames": (C.c_int, [C.c_int, C.c_int]),
     "ts_launch_count": (C.c_int64, [C.c_void_p]),
     "ts_pixelcnn_row_bytes": (C.c_int64, [C.c_void_p]),
     "ts_pixelcnn_staged_row_bytes": (C.c_int64, [C.c_void_p]),

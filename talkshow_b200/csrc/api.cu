@@ -59,6 +59,7 @@ extern "C" void ts_engine_destroy(ts_engine* e) {
   delete e->pix;
   delete e->conv;
   ts::face_destroy(e);
+  ts::mfcc_destroy(e);
   delete e;
 }
 

@@ -133,6 +133,7 @@ struct ts_engine {
   ts::PixelPlan* pix = nullptr;
   ts::ConvStacks* conv = nullptr;
   ts::FaceNet* face = nullptr;
+  void* mfcc_tables = nullptr;  // ts::MfccTables (mfcc.cu)
   ts::Workspace ws;
   std::vector<void*> owned;  // device allocations holding packed weights
   float* upload(const std::vector<float>& h);

@@ -63,5 +63,6 @@ void pixelcnn_generate_act(ts_engine* e, const Act3& aud, const int64_t* label, 
 // idx [B,T,2] -> idx_c [2][B][T]; optionally copies idx to codes_out
 void split_codes(ts_engine* e, const int64_t* idx, int64_t* idx_c, int B, int T, int64_t* codes_out, cudaStream_t s);
 void face_destroy(ts_engine* e);
+void mfcc_destroy(ts_engine* e);
 
 }  // namespace ts

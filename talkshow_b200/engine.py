@@ -111,6 +111,15 @@ class Engine:
     def latent_rows(self, M):
         return self.L.ts_latent_rows(M)
 
+    def mfcc(self, wave, sr):
+        """get_mfcc_ta's transform chain on the device: wave [B,N] mono at ``sr`` Hz -> [B,64,M] (30 fps)."""
+        wave = self._dev(wave, torch.float32)
+        B, N = wave.shape
+        M = self.L.ts_mfcc_frames(N, int(sr))
+        out = torch.empty(B, 64, M, device=self.device)
+        self._check(self.L.ts_mfcc(self.h, _lib.ptr(wave), _lib.ptr(out), B, N, int(sr), self._s()), "ts_mfcc")
+        return out
+
     def audio_encode(self, mfcc):
         """AudioEncoder.forward: [B,64,M] -> [B,256,T]."""
         mfcc = self._dev(mfcc, torch.float32)

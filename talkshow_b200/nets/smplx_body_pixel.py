@@ -35,6 +35,7 @@ class TrainWrapper:
         self.engine = engine or shared_engine(self.device)
         self.noise_device = self.device      # 'cpu' reproduces the CPU reference's RNG stream
         self.noise_per_step = True
+        self.device_mfcc = True              # MFCC features on the device (ts_mfcc); False = host torchaudio chain
         # the reference loads the VQ-VAE checkpoint at construction (:59-62); honour it when present
         vq_path = getattr(self.config.Model, "vq_path", None)
         if vq_path and os.path.exists(vq_path):
@@ -76,9 +77,13 @@ class TrainWrapper:
             return self._infer_continuity(aud_fn, id, fps, sr, B)
         if torch.is_tensor(aud_fn) or isinstance(aud_fn, np.ndarray):
             aud_feat = np.asarray(aud_fn, dtype=np.float32)          # already (M, 64) features
+            mfcc = torch.from_numpy(np.ascontiguousarray(aud_feat.T))[None].repeat(B, 1, 1)   # [B,64,M]
+        elif fps == 30 and sr == 22000 and self.device_mfcc:
+            audio, sr_0 = load_wav(aud_fn)                           # decode on the host, features on the device
+            mfcc = self.engine.mfcc(audio.mean(0, keepdim=True), sr_0).repeat(B, 1, 1)
         else:
             aud_feat = get_mfcc_ta(aud_fn, sr=sr, fps=fps, smlpx=True, type="mfcc", am=am)
-        mfcc = torch.from_numpy(np.ascontiguousarray(aud_feat.T))[None].repeat(B, 1, 1)       # [B,64,M]
+            mfcc = torch.from_numpy(np.ascontiguousarray(aud_feat.T))[None].repeat(B, 1, 1)
         label = torch.tensor([0]) if id is None else id.reshape(-1).repeat(B)[:B] if id.numel() == 1 else id
         return self.generate(mfcc, label).cpu().numpy()
 

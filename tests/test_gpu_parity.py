@@ -224,3 +224,17 @@ def test_face_vs_oracle_10s(face_eng, ckpts):
     err = (got - ref).abs().max().item()
     print("face 10 s max-abs err vs oracle: %.3e" % err)
     assert err <= TOL
+
+
+def test_device_mfcc_matches_torchaudio(eng):
+    """ts_mfcc vs the reference's torchaudio chain (host), 16 kHz and 44.1 kHz sources."""
+    from talkshow_b200.data_utils.utils import mfcc_from_wave
+
+    for sr0, secs in ((16000, 4), (44100, 3), (22000, 2)):
+        wave = synth.synth_wave(2, sr0 * secs, seed=sr0 % 97)
+        ref = np.stack([mfcc_from_wave(wave[b:b + 1], sr0, sr=22000, fps=30).T for b in range(2)])    # [B,64,M]
+        got = eng.mfcc(wave, sr0).cpu().numpy()
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        err = np.abs(got - ref).max()
+        print("device MFCC vs torchaudio (sr0=%d): max-abs %.3e (|ref| max %.1f)" % (sr0, err, np.abs(ref).max()))
+        assert err <= 2e-2
