@@ -49,7 +49,10 @@ struct TcArgs {
   const float* r_lo;
   long r_bs, r_rs;
   int act;
+  const float* a_hi; const float* a_lo;   // raw A arrays (row r = a + r * C), for whole-row L2 prefetches
+  long a_rows;                      // rows in the A arrays
   int nprod;                        // 3 (normal) or 1 (hi*hi only: throughput experiment)
+  int prefetch_rows;                // pair kernel: whole-row L2 prefetch of the A operand one tap ahead
   int cn, cm;                       // cluster shape: cn N-tiles x cm M-tiles share operands by TMA multicast
 };
 
@@ -151,6 +154,100 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
+// Epilogue warps (4..11): TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4.  Drains the K chunks
+// into fp32 registers (round-to-nearest adds), then bias / residual / activation and the (hi, lo) or plain
+// store.  `tempty_addr[buf]` is the shared::cluster address of the barrier that tells the MMA issuer the
+// accumulator buffer is free again (own CTA, or the leader CTA of a pair).
+__device__ __forceinline__ void tc_epilogue(const TcArgs& P, int warp, int lane, int j0, int n0, int nk, uint32_t tmem_base, uint64_t* tfull,
+                                            const uint32_t* tempty_addr) {
+    // ===== epilogue: warps 4..19; TMEM lane quadrant = warp % 4, column quarter = (warp - 4) / 4 =====
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int EC = TC_BN / (TC_EPI_WARPS / 4);     // columns per epilogue thread (128)
+    const int row = quad * 32 + lane;
+    const int j = j0 + row;
+    // GEMM row j <-> padded input row j*stride -> (batch, output step)
+    bool valid = j < P.Rs;
+    int b = 0, t = 0;
+    if (valid) {
+      long in_row = (long)j * P.stride;
+      b = (int)(in_row / P.rows_in);
+      int tin = (int)(in_row - (long)b * P.rows_in) - P.off;
+      valid = b < P.nbatch && tin >= 0 && (tin % P.stride) == 0;
+      t = tin / P.stride;
+      valid = valid && t < P.T_out;
+    }
+    // drain the K chunks into fp32 registers
+    float acc[EC];
+#pragma unroll
+    for (int i = 0; i < EC; ++i) acc[i] = 0.f;
+    const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
+    for (int c = 0; c < nchunks; ++c) {
+      const int buf = c & 1;
+      mb_wait(&tfull[buf], (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int cc = 0; cc < EC / 16; ++cc) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tempty_addr[buf]) : "memory");
+    }
+    float* crow_hi = P.c_hi + (long)b * P.c_bs + (long)t * P.c_rs;
+    float* crow_lo = P.c_lo ? P.c_lo + (long)b * P.c_bs + (long)t * P.c_rs : nullptr;
+    const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
+    const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
+#pragma unroll
+    for (int cc = 0; cc < EC / 32; ++cc) {
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          const int n = n0 + half * EC + cc * 32 + q;
+          if (n >= P.N) break;
+          float o[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float x = acc[cc * 32 + q + u];
+            if (n + u < P.N) {
+              if (P.bias) x += P.bias[n + u];
+              if (rrow_hi) x += rrow_lo ? (rrow_hi[n + u] + rrow_lo[n + u]) : rrow_hi[n + u];
+              x = tc_act(x, P.act);
+            }
+            o[u] = x;
+          }
+          if (n + 3 < P.N) {
+            if (crow_lo) {
+              float4 h, l;
+              h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
+              h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
+              h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
+              h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
+              *reinterpret_cast<float4*>(crow_hi + n) = h;
+              *reinterpret_cast<float4*>(crow_lo + n) = l;
+            } else {
+              *reinterpret_cast<float4*>(crow_hi + n) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          } else {
+            for (int u = 0; u < 4 && n + u < P.N; ++u) {
+              if (crow_lo) {
+                float h = __uint_as_float(__float_as_uint(o[u]) & 0xffffe000u);
+                crow_hi[n + u] = h;
+                crow_lo[n + u] = o[u] - h;
+              } else {
+                crow_hi[n + u] = o[u];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P) {
@@ -245,92 +342,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warps 4..19; TMEM lane quadrant = warp % 4, column quarter = (warp - 4) / 4 =====
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int EC = TC_BN / (TC_EPI_WARPS / 4);     // columns per epilogue thread (128)
-    const int row = quad * 32 + lane;
-    const int j = j0 + row;
-    // GEMM row j <-> padded input row j*stride -> (batch, output step)
-    bool valid = j < P.Rs;
-    int b = 0, t = 0;
-    if (valid) {
-      long in_row = (long)j * P.stride;
-      b = (int)(in_row / P.rows_in);
-      int tin = (int)(in_row - (long)b * P.rows_in) - P.off;
-      valid = b < P.nbatch && tin >= 0 && (tin % P.stride) == 0;
-      t = tin / P.stride;
-      valid = valid && t < P.T_out;
-    }
-    // drain the K chunks into fp32 registers
-    float acc[EC];
-#pragma unroll
-    for (int i = 0; i < EC; ++i) acc[i] = 0.f;
-    const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
-      mb_wait(&tfull[buf], (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int cc = 0; cc < EC / 16; ++cc) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
-      }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(&tempty[buf])) : "memory");
-    }
-    float* crow_hi = P.c_hi + (long)b * P.c_bs + (long)t * P.c_rs;
-    float* crow_lo = P.c_lo ? P.c_lo + (long)b * P.c_bs + (long)t * P.c_rs : nullptr;
-    const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
-    const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
-#pragma unroll
-    for (int cc = 0; cc < EC / 32; ++cc) {
-      if (valid) {
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const int n = n0 + half * EC + cc * 32 + q;
-          if (n >= P.N) break;
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float x = acc[cc * 32 + q + u];
-            if (n + u < P.N) {
-              if (P.bias) x += P.bias[n + u];
-              if (rrow_hi) x += rrow_lo ? (rrow_hi[n + u] + rrow_lo[n + u]) : rrow_hi[n + u];
-              x = tc_act(x, P.act);
-            }
-            o[u] = x;
-          }
-          if (n + 3 < P.N) {
-            if (crow_lo) {
-              float4 h, l;
-              h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
-              h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
-              h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
-              h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
-              *reinterpret_cast<float4*>(crow_hi + n) = h;
-              *reinterpret_cast<float4*>(crow_lo + n) = l;
-            } else {
-              *reinterpret_cast<float4*>(crow_hi + n) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
-            for (int u = 0; u < 4 && n + u < P.N; ++u) {
-              if (crow_lo) {
-                float h = __uint_as_float(__float_as_uint(o[u]) & 0xffffe000u);
-                crow_hi[n + u] = h;
-                crow_lo[n + u] = o[u] - h;
-              } else {
-                crow_hi[n + u] = o[u];
-              }
-            }
-          }
-        }
-      }
-    }
+    const uint32_t te[2] = {s_u32(&tempty[0]), s_u32(&tempty[1])};
+    tc_epilogue(P, warp, lane, j0, n0, nk, tmem_base, tfull, te);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -338,6 +351,157 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+  }
+}
+
+// ---- CTA-pair variant (cta_group::2) -------------------------------------------------------------
+// Two CTAs of a (1,2) cluster form one 256 x 256 tile: each CTA stages its own 128 A rows and HALF of the
+// 256-row B tile (64 KB per k-block instead of 96 KB: the per-SM L2->smem delivery that limits the
+// single-CTA kernel), the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves of B,
+// and each CTA's epilogue drains its own 128 TMEM lanes.  TMA completions of both CTAs land on the leader's
+// `full` barrier; tcgen05.commit multicasts the `empty` / `tfull` arrivals to both CTAs.
+constexpr int T2_STAGES = 3;
+constexpr int T2_BHALF = TC_BN / 2 * TC_BK * 4;                      // 16 KB: 128 rows of the B tile
+constexpr int T2_STAGE_BYTES = 2 * TC_A_BYTES + 2 * T2_BHALF;      // 64 KB
+constexpr int T2_SMEM = T2_STAGES * T2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void tma_3d_2sm(void* dst, const CUtensorMap* m, int c0, int c1, int c2, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   s_u32(dst)),
+               "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(leader_bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_2d_2sm(void* dst, const CUtensorMap* m, int c0, int c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   s_u32(dst)),
+               "l"(m), "r"(c0), "r"(c1), "r"(leader_bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a), "l"(b),
+      "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+                const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE_BYTES);
+  uint64_t* empty = full + T2_STAGES;
+  uint64_t* tfull = empty + T2_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair
+  // 1-D grid, (2,1,1) clusters: blockIdx.x = 2 * (n_tile + tiles_n * m_pair) + member  (P.cn carries tiles_n);
+  // the pair covers M tiles 2*m_pair and 2*m_pair+1 of one N tile, N tiles vary fastest (A row blocks shared in L2)
+  const int lin = blockIdx.x >> 1, nt = lin % P.cn, mp = lin / P.cn;
+  const int j0 = (2 * mp + (int)rank) * TC_BM, n0 = nt * TC_BN;
+  const int nk = P.taps * P.cblocks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < T2_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    mb_init(&tfull[0], 1); mb_init(&tfull[1], 1);
+    mb_init(&tempty[0], 2 * TC_EPI_WARPS); mb_init(&tempty[1], 2 * TC_EPI_WARPS);   // epilogue warps of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_lo) : "memory");
+  }
+  if (warp == 1) {  // pair-wide TMEM allocation (same warp id, same slot offset in both CTAs)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(2 * TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // Whole-row L2 prefetch: a tap's A rows (C*4 bytes contiguous each) are pulled into L2 as full rows one
+    // tap ahead, so DRAM sees 2-4 KB bursts instead of the 128-byte pieces the k-block boxes would request
+    auto prefetch_tap = [&](int tap) {
+      if (tap >= P.taps) return;
+      const uint32_t bytes = (uint32_t)P.C * 4u;
+      for (int r = lane; r < TC_BM; r += 32) {
+        const long row = (long)(j0 + r + tap / P.stride) * P.stride + tap % P.stride;
+        if (row < P.a_rows) {
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.a_hi + row * P.C), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.a_lo + row * P.C), "r"(bytes) : "memory");
+        }
+      }
+    };
+    if (P.prefetch_rows) { prefetch_tap(0); prefetch_tap(1); }
+    __syncwarp();
+    for (int kbp = 0; kbp < nk; kbp += P.cblocks) {   // one iteration per tap
+      if (P.prefetch_rows && kbp > 0) prefetch_tap(kbp / P.cblocks + 1);
+      __syncwarp();
+      if (lane == 0)
+      for (int kb = kbp; kb < kbp + P.cblocks; ++kb) {
+        const int st = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
+        mb_wait(&empty[st], ph ^ 1);
+        const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
+        unsigned char* base = smem + st * T2_STAGE_BYTES;
+        if (rank == 0) mb_expect(&full[st], 2 * T2_STAGE_BYTES);            // bytes of both CTAs land on the leader's barrier
+        const uint32_t lbar = s_u32(&full[st]) & 0xFEFFFFFFu;               // peer bit cleared -> CTA 0 of the pair
+        const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
+        tma_3d_2sm(base, &mA_hi, c0, c1, c2, lbar);
+        tma_3d_2sm(base + TC_A_BYTES, &mA_lo, c0, c1, c2, lbar);
+        const int kcol = tap * P.C + cb * TC_BK, nrow = n0 + (int)rank * (TC_BN / 2);
+        tma_2d_2sm(base + 2 * TC_A_BYTES, &mB_hi, kcol, nrow, lbar);
+        tma_2d_2sm(base + 2 * TC_A_BYTES + T2_BHALF, &mB_lo, kcol, nrow, lbar);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ===== MMA issuer: leader CTA only =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
+        const int chunk = kb / TC_CHUNK, kin = kb - chunk * TC_CHUNK, buf = chunk & 1;
+        if (kin == 0) {
+          mb_wait(&tempty[buf], ((chunk >> 1) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        mb_wait(&full[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = s_u32(smem + st * T2_STAGE_BYTES), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + T2_BHALF;
+        const uint32_t d = tmem_base + buf * TC_BN;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t o = k * 32;
+          umma2_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+          umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+          umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+        }
+        umma2_commit(&empty[st]);
+        if (kin == TC_CHUNK - 1 || kb == nk - 1) umma2_commit(&tfull[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // the "buffer drained" arrivals of both CTAs go to the leader's tempty barriers
+    uint32_t te[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(te[i]) : "r"(s_u32(&tempty[i])), "r"(0));
+    tc_epilogue(P, warp, lane, j0, n0, nk, tmem_base, tfull, te);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
   }
 }
 
@@ -423,11 +587,13 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
     cn = (tiles_n % 4 == 0) ? 4 : (tiles_n % 2 == 0) ? 2 : 1;
     cm = tiles_m >= 2 ? 2 : 1;
   }
-  cuuint32_t abox[3] = {TC_BK, 1, (cuuint32_t)(TC_BM / cn)};
+  const bool pair = e->tc_pair;   // CTA-pair kernel: (1,2) cluster, each CTA loads half of the B tile
+  if (pair) { cn = 1; cm = 2; }
+  cuuint32_t abox[3] = {TC_BK, 1, (cuuint32_t)(pair ? TC_BM : TC_BM / cn)};
   CUtensorMap mAh = make_map(base_hi, 3, adims, astr, abox), mAl = make_map(base_lo, 3, adims, astr, abox);
   cuuint64_t bdims[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
   cuuint64_t bstr[1] = {(cuuint64_t)L.K * 4};
-  cuuint32_t bbox[2] = {TC_BK, (cuuint32_t)(TC_BN / cm)};
+  cuuint32_t bbox[2] = {TC_BK, (cuuint32_t)(TC_BN / cm)};   // pair: cm == 2 -> 128-row halves
   CUtensorMap mBh = make_map(L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(L.W_lo, 2, bdims, bstr, bbox);
   TcArgs P;
   P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
@@ -439,23 +605,32 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.r_lo = (res && res->lo) ? res->row_lo(0, 0) : nullptr;
   P.r_bs = res ? res->bstride() : 0; P.r_rs = res ? res->C : 0;
   P.act = act;
-  P.cn = cn; P.cm = cm;
+  P.cn = pair ? tiles_n : cn; P.cm = cm;
   { const char* np = getenv("TS_TC_NPROD"); P.nprod = (np && np[0] == '1') ? 1 : 3; }
+  P.a_hi = base_hi; P.a_lo = base_lo; P.a_rows = R;
+  // whole-row L2 prefetch measured slower (96 vs 89 ms per face pass): off unless TS_TC_ROWPF=1
+  { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1') ? 1 : 0; }
   static bool attr = false;
-  if (!attr) { TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); attr = true; }
+  if (!attr) {
+    TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    attr = true;
+  }
   // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
   dim3 grid((unsigned)(((tiles_n + cn - 1) / cn) * cn), (unsigned)(((tiles_m + cm - 1) / cm) * cm));
+  if (pair) grid = dim3((unsigned)(2 * tiles_n * ((tiles_m + 1) / 2)), 1, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.dynamicSmemBytes = pair ? T2_SMEM : TC_SMEM;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = cn; at[0].val.clusterDim.y = cm; at[0].val.clusterDim.z = 1;
+  at[0].val.clusterDim.x = pair ? 2 : cn; at[0].val.clusterDim.y = pair ? 1 : cm; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));
+  if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel, mAh, mAl, mBh, mBl, P));
+  else TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));
   e->launches++;
   TS_CUDA(cudaGetLastError());
 }
@@ -480,8 +655,9 @@ using namespace ts;
 
 extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   if (!e) return TS_ERR_INVALID;
-  e->use_tc = enable != 0;
-  e->tc_multicast = enable != 2;   // 2 = tensor cores without cluster multicast (A/B measurements)
+  e->use_tc = enable != 0;         // 1 = 128x256 single-CTA kernel (default)
+  e->tc_multicast = enable == 2;   // 2 = + (n x 2) cluster with TMA multicast of the operand boxes
+  e->tc_pair = enable == 3;        // 3 = CTA-pair (cta_group::2) 256x256 kernel
   return TS_OK;
 }
 
