@@ -130,9 +130,10 @@ int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, flo
  * mode 0 = fp32 FFMA kernel, mode 1 = tcgen05 3xTF32 tensor-core kernel (K % 32 == 0). */
 int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N,
                   int K, int act, void* stream);
-/* 1 (default): face / VQ-decoder contractions run on the tcgen05 3xTF32 tensor-core kernel (128x256 tile);
- * 2: same with cluster TMA multicast of the operand boxes; 3: CTA-pair (cta_group::2) 256x256 variant;
- * 0: everything on the fp32 FFMA kernel.  All four are parity-tested; 1-3 measure within 3 % of each other. */
+/* Dense-contraction kernel selection (all parity-tested):
+ * 1 (default) / 3: tcgen05 3xTF32 kernel, CTA pair (cta_group::2) 256x256 tile;
+ * 4: tcgen05 3xTF32 kernel, single CTA 128x256 tile; 2: same in clusters with TMA multicast of the operand boxes;
+ * 0: everything on the fp32 FFMA kernel. */
 int ts_set_tensor_cores(ts_engine* e, int enable);
 /* 0 = v1 persistent cooperative kernel (grid barrier), 1 = v1 one launch per stage (debug cross-check),
  * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only */

@@ -128,7 +128,7 @@ struct ts_engine {
   std::string err;
   int64_t launches = 0;
   int pixel_mode = 0;
-  bool tc_pair = false;      // CTA-pair (cta_group::2) tensor-core kernel
+  bool tc_pair = true;       // CTA-pair (cta_group::2) 256x256 tensor-core kernel (default)
   bool tc_multicast = false;  // share operand boxes inside a thread-block cluster by TMA multicast
   bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows
   ts::PixelPlan* pix = nullptr;

@@ -154,99 +154,108 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
-// Epilogue warps (4..11): TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4.  Drains the K chunks
-// into fp32 registers (round-to-nearest adds), then bias / residual / activation and the (hi, lo) or plain
-// store.  `tempty_addr[buf]` is the shared::cluster address of the barrier that tells the MMA issuer the
-// accumulator buffer is free again (own CTA, or the leader CTA of a pair).
-__device__ __forceinline__ void tc_epilogue(const TcArgs& P, int warp, int lane, int j0, int n0, int nk, uint32_t tmem_base, uint64_t* tfull,
-                                            const uint32_t* tempty_addr) {
-    // ===== epilogue: warps 4..19; TMEM lane quadrant = warp % 4, column quarter = (warp - 4) / 4 =====
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int EC = TC_BN / (TC_EPI_WARPS / 4);     // columns per epilogue thread (128)
-    const int row = quad * 32 + lane;
+// Epilogue warps (4..11): TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4.
+//  1. drain: after every K chunk the warp adds its 32 lanes x 128 columns of the TMEM accumulator into
+//     fp32 registers (round-to-nearest) and frees the buffer (`tempty_addr[buf]`: shared::cluster address of
+//     the MMA issuer's barrier — own CTA, or the leader CTA of a pair);
+//  2. the 128 x 256 tile is parked in shared memory (the operand ring is idle by then) and written out by
+//     a compact loop with threads along N: coalesced bias / residual loads and float4 stores, and ~150
+//     instructions of code instead of a 10k-instruction unrolled epilogue (the first version spent 30 % of
+//     its warp samples in instruction-fetch stalls).
+constexpr int TC_SLD = TC_BN + 4;   // padded row of the parked tile (floats)
+__device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem, int warp, int lane, int j0, int n0, int nk, uint32_t tmem_base,
+                                            uint64_t* tfull, const uint32_t* tempty_addr) {
+  const int quad = warp & 3;
+  const int half = (warp - 4) >> 2;
+  constexpr int EC = TC_BN / 2;
+  const int row = quad * 32 + lane;
+  float acc[EC];
+#pragma unroll
+  for (int i = 0; i < EC; ++i) acc[i] = 0.f;
+  const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    mb_wait(&tfull[buf], (c >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int cc = 0; cc < EC / 16; ++cc) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tempty_addr[buf]) : "memory");
+  }
+  // ---- park the tile: S[row][col], plus the (batch, step) of every GEMM row -----------------------------
+  float* S = reinterpret_cast<float*>(smem);
+  int* rowb = reinterpret_cast<int*>(S + TC_BM * TC_SLD);
+  int* rowt = rowb + TC_BM;
+#pragma unroll
+  for (int c = 0; c < EC; c += 4)
+    *reinterpret_cast<float4*>(&S[row * TC_SLD + half * EC + c]) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+  if (half == 0) {  // GEMM row j <-> padded input row j*stride -> (batch, output step)
     const int j = j0 + row;
-    // GEMM row j <-> padded input row j*stride -> (batch, output step)
-    bool valid = j < P.Rs;
-    int b = 0, t = 0;
-    if (valid) {
-      long in_row = (long)j * P.stride;
-      b = (int)(in_row / P.rows_in);
-      int tin = (int)(in_row - (long)b * P.rows_in) - P.off;
-      valid = b < P.nbatch && tin >= 0 && (tin % P.stride) == 0;
-      t = tin / P.stride;
-      valid = valid && t < P.T_out;
+    int b = -1, t = 0;
+    if (j < P.Rs) {
+      const long in_row = (long)j * P.stride;
+      const int bb = (int)(in_row / P.rows_in);
+      const int tin = (int)(in_row - (long)bb * P.rows_in) - P.off;
+      if (bb < P.nbatch && tin >= 0 && (tin % P.stride) == 0 && tin / P.stride < P.T_out) { b = bb; t = tin / P.stride; }
     }
-    // drain the K chunks into fp32 registers
-    float acc[EC];
+    rowb[row] = b;
+    rowt[row] = t;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+  // ---- write out: thread -> 4 consecutive columns, consecutive threads -> consecutive columns ----------------
+  const int et = threadIdx.x - 128;
+#pragma unroll 1
+  for (int i = et; i < TC_BM * (TC_BN / 4); i += 256) {
+    const int r = i / (TC_BN / 4), c4 = (i - r * (TC_BN / 4)) * 4;
+    const int n = n0 + c4;
+    const int b = rowb[r];
+    if (b < 0 || n >= P.N) continue;
+    const int t = rowt[r];
+    const float4 sv = *reinterpret_cast<const float4*>(&S[r * TC_SLD + c4]);
+    float o[4] = {sv.x, sv.y, sv.z, sv.w};
+    const long coff = (long)b * P.c_bs + (long)t * P.c_rs + n;
+    const long roff = (long)b * P.r_bs + (long)t * P.r_rs + n;
 #pragma unroll
-    for (int i = 0; i < EC; ++i) acc[i] = 0.f;
-    const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
-    for (int c = 0; c < nchunks; ++c) {
-      const int buf = c & 1;
-      mb_wait(&tfull[buf], (c >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int cc = 0; cc < EC / 16; ++cc) {
-        uint32_t v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
+    for (int q = 0; q < 4; ++q) {
+      if (n + q < P.N) {
+        float x = o[q];
+        if (P.bias) x += P.bias[n + q];
+        if (P.r_hi) x += P.r_lo ? (P.r_hi[roff + q] + P.r_lo[roff + q]) : P.r_hi[roff + q];
+        o[q] = tc_act(x, P.act);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tempty_addr[buf]) : "memory");
     }
-    float* crow_hi = P.c_hi + (long)b * P.c_bs + (long)t * P.c_rs;
-    float* crow_lo = P.c_lo ? P.c_lo + (long)b * P.c_bs + (long)t * P.c_rs : nullptr;
-    const float* rrow_hi = P.r_hi ? P.r_hi + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
-    const float* rrow_lo = P.r_lo ? P.r_lo + (long)b * P.r_bs + (long)t * P.r_rs : nullptr;
-#pragma unroll
-    for (int cc = 0; cc < EC / 32; ++cc) {
-      if (valid) {
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          const int n = n0 + half * EC + cc * 32 + q;
-          if (n >= P.N) break;
-          float o[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float x = acc[cc * 32 + q + u];
-            if (n + u < P.N) {
-              if (P.bias) x += P.bias[n + u];
-              if (rrow_hi) x += rrow_lo ? (rrow_hi[n + u] + rrow_lo[n + u]) : rrow_hi[n + u];
-              x = tc_act(x, P.act);
-            }
-            o[u] = x;
-          }
-          if (n + 3 < P.N) {
-            if (crow_lo) {
-              float4 h, l;
-              h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
-              h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
-              h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
-              h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
-              *reinterpret_cast<float4*>(crow_hi + n) = h;
-              *reinterpret_cast<float4*>(crow_lo + n) = l;
-            } else {
-              *reinterpret_cast<float4*>(crow_hi + n) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
-            for (int u = 0; u < 4 && n + u < P.N; ++u) {
-              if (crow_lo) {
-                float h = __uint_as_float(__float_as_uint(o[u]) & 0xffffe000u);
-                crow_hi[n + u] = h;
-                crow_lo[n + u] = o[u] - h;
-              } else {
-                crow_hi[n + u] = o[u];
-              }
-            }
-          }
+    if (n + 3 < P.N) {
+      if (P.c_lo) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
+        h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
+        h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
+        h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
+        *reinterpret_cast<float4*>(P.c_hi + coff) = h;
+        *reinterpret_cast<float4*>(P.c_lo + coff) = l;
+      } else {
+        *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      for (int q = 0; q < 4 && n + q < P.N; ++q) {
+        if (P.c_lo) {
+          const float h = __uint_as_float(__float_as_uint(o[q]) & 0xffffe000u);
+          P.c_hi[coff + q] = h;
+          P.c_lo[coff + q] = o[q] - h;
+        } else {
+          P.c_hi[coff + q] = o[q];
         }
       }
     }
   }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -343,7 +352,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
     }
   } else if (warp >= 4) {
     const uint32_t te[2] = {s_u32(&tempty[0]), s_u32(&tempty[1])};
-    tc_epilogue(P, warp, lane, j0, n0, nk, tmem_base, tfull, te);
+    tc_epilogue(P, smem, warp, lane, j0, n0, nk, tmem_base, tfull, te);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -494,7 +503,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
 #pragma unroll
     for (int i = 0; i < 2; ++i)
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(te[i]) : "r"(s_u32(&tempty[i])), "r"(0));
-    tc_epilogue(P, warp, lane, j0, n0, nk, tmem_base, tfull, te);
+    tc_epilogue(P, smem, warp, lane, j0, n0, nk, tmem_base, tfull, te);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -655,9 +664,10 @@ using namespace ts;
 
 extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   if (!e) return TS_ERR_INVALID;
-  e->use_tc = enable != 0;         // 1 = 128x256 single-CTA kernel (default)
-  e->tc_multicast = enable == 2;   // 2 = + (n x 2) cluster with TMA multicast of the operand boxes
-  e->tc_pair = enable == 3;        // 3 = CTA-pair (cta_group::2) 256x256 kernel
+  e->use_tc = enable != 0;
+  e->tc_pair = enable == 1 || enable == 3;   // 1 (default) / 3 = CTA-pair (cta_group::2) 256x256 kernel
+  e->tc_multicast = enable == 2;             // 2 = single-CTA 128x256 kernel in (n x 2) clusters with TMA multicast
+                                             // 4 = single-CTA 128x256 kernel, no cluster
   return TS_OK;
 }
 
