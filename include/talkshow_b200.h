@@ -138,6 +138,10 @@ int ts_set_tensor_cores(ts_engine* e, int enable);
 /* 0 = v1 persistent cooperative kernel (grid barrier), 1 = v1 one launch per stage (debug cross-check),
  * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
+/* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
+ * stack multiplied together at load, layer-0 gate of column 1 gathered from a code table), 0 = plain 84-stage plan
+ * (one stage per reference conv).  Both evaluate GatedPixelCNN.forward exactly up to fp32 rounding order. */
+int ts_set_pixelcnn_fusion(ts_engine* e, int on);
 
 #ifdef __cplusplus
 }

@@ -72,6 +72,12 @@ extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
   return TS_OK;
 }
 
+extern "C" int ts_set_pixelcnn_fusion(ts_engine* e, int on) {
+  if (!e) return TS_ERR_INVALID;
+  e->pixel_fusion = on != 0;
+  return TS_OK;
+}
+
 // ---- pose assembly: scripts/demo.py:182-229 + data_utils/lower_body.py:68-87 -------------------
 __constant__ float c_lower_pose[33] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 3.0747f, -0.0158f, -0.0152f,
     -1.1826512813568115f, 0.23866955935955048f, 0.15146760642528534f, -1.2604516744613647f, -0.3160211145877838f,

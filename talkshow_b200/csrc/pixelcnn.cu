@@ -27,6 +27,35 @@ struct Job {
   bool pairs;
 };
 
+// Fused plan: every linear stage of the horizontal stack is folded into the gate matmul that consumes it
+// (W_next (W_res g + b + x) = (W_next W_res) g + W_next b + W_next x), the layer-0 gate of column 0 (no
+// matmul) rides in the last vertical stage, and the layer-0 gate of column 1 is a table lookup done by the
+// sampler itself: 16 + 2 x 18 = 52 dependent stages per row instead of 84.
+static std::vector<std::vector<Job>> build_stages_fused(int L) {
+  const int D = PIX_D;
+  std::vector<std::vector<Job>> st;
+  st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});
+  for (int l = 1; l < L; ++l) {
+    std::vector<Job> j = {{EPI_VERT, l, 0, 2 * D, 4 * D, 1, true}, {EPI_VERT, l, 1, 2 * D, 4 * D, 1, true}};
+    if (l >= 2) j.push_back({EPI_V2H, l - 1, 0, 2 * D, 2 * D, 2, false});
+    if (l == 1) j.push_back({EPI_HGATE, 0, 0, 2 * D, 0, 1, true});   // G_0 of column 0: v2h_0 (previous stage) + class term only
+    st.push_back(j);
+  }
+  for (int c = 0; c < 2; ++c) {
+    std::vector<Job> j = {{EPI_HRESF, 0, c, D, D, 1, false}};
+    if (c == 0) j.push_back({EPI_V2H, L - 1, 0, 2 * D, 2 * D, 2, false});
+    st.push_back(j);
+    st.push_back({{EPI_HGATE, 1, c, 2 * D, c ? 2 * D : D, 1, true}});
+    for (int l = 2; l < L; ++l)
+      st.push_back({{EPI_HGATE2, l, c, 2 * D, c ? 3 * D : 2 * D, 1, true}, {EPI_HRES, l - 1, c, D, D, 1, false}});
+    st.push_back({{EPI_OUT1F, 0, c, 512, 2 * D, 1, false}});
+    st.push_back({{EPI_OUT2, 0, c, PIX_NCODE, 512, 1, false}});
+    st.push_back({{EPI_SAMPLE, 0, c, 0, c == 0 ? 1 : 0, 1, false}});     // K = 1: also emit G_0 of column 1
+  }
+  return st;
+}
+
 static std::vector<std::vector<Job>> build_stages(int L) {
   const int D = PIX_D;
   std::vector<std::vector<Job>> st;
@@ -65,7 +94,7 @@ static PixLayout make_layout(int L) {
   a.XV = take(L * 2 * 2);
   a.HV = take(2 * 2 * 2);
   a.V2H = take(L * 2 * 2);
-  a.G = take(1);
+  a.G = take(2);     // gate output of layer l lives in slot l & 1
   a.XHP = take(1);
   a.XH = take(2 * (L + 1));
   a.Y = take(2);
@@ -81,6 +110,34 @@ struct WeightSrc {
   int L;
   std::vector<const float*> vs, vsb, v2h, v2hb, hs, hsb, hr, hrb;
   const float *fv, *fh, *o1, *o1b, *o2, *o2b;
+  // fused plan: products of adjacent linear maps, accumulated in fp64 and rounded once
+  std::vector<std::vector<float>> Mh, bh;   // [l]: horiz_stack_l(tap 1) . horiz_resid_{l-1}  [2D][D], and . bias  [2D]
+  std::vector<float> Mf, bf, Mo, bo;        // fusion_h(x half) . horiz_resid_0 [D][D];  output_conv.0 . horiz_resid_{L-1} [512][D]
+  static void compose(const float* A, int lda, int astride, int N, const float* Bm, const float* bb, int D,
+                      std::vector<float>& M, std::vector<float>& mb) {
+    // M[n][j] = sum_i A[n*lda + i*astride] * Bm[i*D + j];  mb[n] = sum_i A[..] * bb[i]
+    M.assign((size_t)N * D, 0.f); mb.assign(N, 0.f);
+    std::vector<double> acc(D);
+    for (int n = 0; n < N; ++n) {
+      std::fill(acc.begin(), acc.end(), 0.0);
+      double ab = 0.0;
+      for (int i = 0; i < D; ++i) {
+        const double a = A[(size_t)n * lda + (size_t)i * astride];
+        const float* brow = Bm + (size_t)i * D;
+        for (int j = 0; j < D; ++j) acc[j] += a * (double)brow[j];
+        ab += a * (double)bb[i];
+      }
+      for (int j = 0; j < D; ++j) M[(size_t)n * D + j] = (float)acc[j];
+      mb[n] = (float)ab;
+    }
+  }
+  void build_fused() {
+    const int D = PIX_D;
+    Mh.resize(L); bh.resize(L);
+    for (int l = 2; l < L; ++l) compose(hs[l] + 1, 2 * D, 2, 2 * D, hr[l - 1], hrb[l - 1], D, Mh[l], bh[l]);
+    compose(fh, 2 * D, 1, D, hr[0], hrb[0], D, Mf, bf);
+    compose(o1, D, 1, 512, hr[L - 1], hrb[L - 1], D, Mo, bo);
+  }
   WeightSrc(const Ckpt& c, int L_) : ck(c), L(L_) {
     const int D = PIX_D;
     for (int l = 0; l < L; ++l) {
@@ -125,6 +182,11 @@ struct WeightSrc {
         return hs[l][((size_t)ch * D + ci) * 2 + tap];
       }
       case EPI_HRES: return hr[l][(size_t)ch * D + k];
+      case EPI_HRESF: return Mf[(size_t)ch * D + k];
+      case EPI_HGATE2:   // seg 0 = G_{l-1} (composed), seg 1 = x_h[l-1] of this column (tap 1), seg 2 = x_h[l] of column 0 (tap 0)
+        if (sidx == 0) return Mh[l][(size_t)ch * D + ci];
+        return hs[l][((size_t)ch * D + ci) * 2 + (sidx == 1 ? 1 : 0)];
+      case EPI_OUT1F: return sidx == 0 ? Mo[(size_t)ch * D + ci] : o1[(size_t)ch * D + ci];
       case EPI_OUT1: return o1[(size_t)ch * D + k];
       case EPI_OUT2: return o2[(size_t)ch * 512 + k];
     }
@@ -137,6 +199,9 @@ struct WeightSrc {
       case EPI_V2H: return v2hb[l][ch];
       case EPI_HGATE: return hsb[l][ch];
       case EPI_HRES: return hrb[l][ch];
+      case EPI_HRESF: return bf[ch];
+      case EPI_HGATE2: return hsb[l][ch] + bh[l][ch];
+      case EPI_OUT1F: return o1b[ch] + bo[ch];
       case EPI_OUT1: return o1b[ch];
       case EPI_OUT2: return o2b[ch];
     }
@@ -155,7 +220,7 @@ static Layer pack_1x1(ts_engine* e, const float* w, int ldw, int koff, const flo
   return L;
 }
 
-static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
+static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
   const int D = PIX_D;
   const ts_tensor* emb = ck.get("embedding.weight");
   if (emb->ndim != 2 || emb->shape[1] != D || emb->shape[0] != PIX_NCODE)
@@ -173,25 +238,52 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
   P->nclasses = ncls;
   P->lay = make_layout(L);
   if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);
-  auto stages = build_stages(L);
+  fused = fused && L >= 3;
+  P->fused = fused;
+  auto stages = fused ? build_stages_fused(L) : build_stages(L);
   P->nstages = (int)stages.size();
+  if (P->nstages > 160) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d stages per row (> 160)", P->nstages);
   P->table.assign((size_t)P->nstages * P->ncta, PixTask{0, 0, 0, 0, 0, 0, 0, 0});
   WeightSrc ws(ck, L);
+  if (fused) ws.build_fused();
   int64_t dense = 0;
+  int t0_ofs = 0;
+  if (fused) {
+    // T0[code][jr] = bias + horiz_stack_0(tap 0) . embedding[code]: the layer-0 gate pre-activation of column 1
+    // depends on the sampled column-0 code only -> a 2048 x 512 table the sampler gathers from (kept in the blob
+    // so that the exported plan is self-contained)
+    const float* ew = ck.f32("embedding.weight", {PIX_NCODE, D});
+    const Job j0{EPI_HGATE, 0, 1, 2 * D, D, 1, true};
+    P->blob.resize((size_t)PIX_NCODE * 2 * D);
+    std::vector<float> wrow((size_t)2 * D * D), brow(2 * D);
+    for (int jr = 0; jr < 2 * D; ++jr) {
+      brow[jr] = ws.bias(j0, jr);
+      for (int k = 0; k < D; ++k) wrow[(size_t)jr * D + k] = ws.w(j0, jr, k);
+    }
+    for (int code = 0; code < PIX_NCODE; ++code)
+      for (int jr = 0; jr < 2 * D; ++jr) {
+        double a = 0.0;
+        for (int k = 0; k < D; ++k) a += (double)wrow[(size_t)jr * D + k] * (double)ew[(size_t)code * D + k];
+        P->blob[(size_t)code * 2 * D + jr] = (float)(a + (double)brow[jr]);
+      }
+  }
+  const size_t table_floats = P->blob.size();
   for (int s = 0; s < P->nstages; ++s) {
     auto& jobs = stages[s];
     if (jobs[0].epi == EPI_SAMPLE) {
-      for (int c = 0; c < P->ncta; ++c) P->table[(size_t)s * P->ncta + c] = PixTask{EPI_SAMPLE, 0, jobs[0].col, 0, 0, 0, 0, 0};
+      for (int c = 0; c < P->ncta; ++c)
+        P->table[(size_t)s * P->ncta + c] = PixTask{EPI_SAMPLE, 0, jobs[0].col, 0, 0, jobs[0].K ? t0_ofs : 0, jobs[0].K, 0};
       continue;
     }
     // CTAs per job proportional to FMA cost
     std::vector<double> cost;
     double tot = 0;
-    for (auto& j : jobs) { double c = (double)j.nrows * std::max(j.K, 256) * j.ncol; cost.push_back(c); tot += c; }
+    for (auto& j : jobs) { double c = (double)j.nrows * (j.K ? std::max(j.K, 256) : 16) * j.ncol; cost.push_back(c); tot += c; }
     std::vector<int> nc(jobs.size()), lo(jobs.size());
     int used = 0;
     for (size_t i = 0; i < jobs.size(); ++i) {
-      lo[i] = (jobs[i].nrows + PIX_MAXROWS - 1) / PIX_MAXROWS;  // rows per CTA must stay <= PIX_MAXROWS
+      const int cap = jobs[i].K ? PIX_MAXROWS : 4 * PIX_MAXROWS;  // matmul rows per CTA <= PIX_MAXROWS; epilogue-only tasks: 64
+      lo[i] = (jobs[i].nrows + cap - 1) / cap;
       nc[i] = std::max(lo[i], (int)std::floor(P->ncta * cost[i] / tot));
       used += nc[i];
     }
@@ -214,7 +306,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
         if (nu > 0) {
           t.epi = j.epi; t.layer = j.layer; t.col = j.col;
           t.row0 = u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
-          if (t.nrows > PIX_MAXROWS) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per CTA (> %d) with %d SMs", t.nrows, PIX_MAXROWS, P->ncta);
+          if (t.K > 0 && t.nrows > PIX_MAXROWS) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per CTA (> %d) with %d SMs", t.nrows, PIX_MAXROWS, P->ncta);
           size_t sz = (size_t)(t.K + 1) * t.rpad;
           if (sz > (size_t)PIX_WBUF) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: task blob %zu floats > staging buffer", sz);
           t.wofs = (int)P->blob.size();
@@ -247,7 +339,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck) {
     w += (int64_t)512 * D + 512 + (int64_t)PIX_NCODE * 512 + PIX_NCODE;
     P->row_bytes = 4 * w;
   }
-  P->staged_row_bytes = 4 * ((int64_t)P->blob.size() + 3LL * D * D);
+  P->staged_row_bytes = 4 * ((int64_t)(P->blob.size() - table_floats) + 3LL * D * D);
   (void)dense;
 
   // audio terms: a = embedding_aud(aud); AUDV = fusion_v[:, D:]*a + b_v; AUDH = fusion_h[:, D:]*a + b_h
@@ -289,7 +381,7 @@ struct PixArgs {
   float* logits_out;   // [2*(Ttot-log_r0)][B][2048] or null
   unsigned* barrier;
   PixLayout lay;
-  int B, T0, Ttot, log_r0, L, nstages, ncta;
+  int B, T0, Ttot, log_r0, L, nstages, ncta, fused;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -344,7 +436,7 @@ __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) 
 
 __device__ __forceinline__ bool task_active(const PixTask& t, int r, int log_r0) {
   if (t.epi == EPI_IDLE) return false;
-  if (t.epi == EPI_OUT1 || t.epi == EPI_OUT2) return r >= log_r0;
+  if (t.epi == EPI_OUT1 || t.epi == EPI_OUT2 || t.epi == EPI_OUT1F) return r >= log_r0;
   return true;
 }
 __device__ __forceinline__ uint32_t task_bytes(const PixTask& t) { return (uint32_t)((t.K + 1) * t.rpad) * 4u; }
@@ -375,7 +467,18 @@ __device__ __forceinline__ int resolve_segments(const PixTask& t, int pass, int 
       if (t.col == 0) return 1;
       seg[1] = a.XH + (1 * (L + 1) + t.layer) * PIX_SEG;
       return 2;
-    case EPI_HRES: seg[0] = a.G; return 1;
+    case EPI_HRES: seg[0] = a.G + (t.layer & 1) * PIX_SEG; return 1;
+    case EPI_HRESF: seg[0] = a.G; return 1;
+    case EPI_HGATE2:
+      seg[0] = a.G + ((t.layer - 1) & 1) * PIX_SEG;
+      seg[1] = a.XH + (t.col * (L + 1) + t.layer - 1) * PIX_SEG;
+      if (t.col == 0) return 2;
+      seg[2] = a.XH + (0 * (L + 1) + t.layer) * PIX_SEG;
+      return 3;
+    case EPI_OUT1F:
+      seg[0] = a.G + ((L - 1) & 1) * PIX_SEG;
+      seg[1] = a.XH + (t.col * (L + 1) + L - 1) * PIX_SEG;
+      return 2;
     case EPI_FUSEH: seg[0] = a.XHP; return 1;
     case EPI_OUT1: seg[0] = a.XH + (t.col * (L + 1) + L) * PIX_SEG; return 1;
     case EPI_OUT2: seg[0] = a.Y; seg[1] = a.Y + PIX_SEG; return 2;
@@ -419,6 +522,58 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
     *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
 }
 
+// Same partial products (same per-accumulator summation order -> bit-identical), software-pipelined: the
+// activation loads form a ring of 4 groups x 8 rows; a group is re-issued for k+32 as soon as its FMAs are
+// done, so every warp keeps 24-32 L2 loads in flight while it computes instead of alternating a load burst
+// and an FMA burst (which also synchronises the L2 traffic of all 148 CTAs into bursts).
+template <int RC, int G>
+__device__ __forceinline__ void mm_rows_pipe(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
+                                             float* red, int warp, int lane) {
+  float2 acc[4 * RC];
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j) acc[j] = make_float2(0.f, 0.f);
+  const int kper = K >> 3;  // multiple of 32
+  const int slice = (warp + blockIdx.x) & 7;
+  const int kbeg = slice * kper, kend = kbeg + kper;
+  constexpr int GS = 8;
+  float2 x[G][GS];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {   // kper is a multiple of G * GS = 32
+    const int k = kbeg + g * GS;
+    const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+#pragma unroll
+    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+  }
+  for (int k0 = kbeg; k0 < kend; k0 += G * GS) {
+    const bool more = k0 + G * GS < kend;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int u = 0; u < GS; ++u) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wsm + (size_t)(k0 + g * GS + u) * (4 * RC));
+        const float2 xv = x[g][u];
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+          float4 w = w4[rc];
+          acc[rc * 4 + 0].x = fmaf(w.x, xv.x, acc[rc * 4 + 0].x); acc[rc * 4 + 0].y = fmaf(w.x, xv.y, acc[rc * 4 + 0].y);
+          acc[rc * 4 + 1].x = fmaf(w.y, xv.x, acc[rc * 4 + 1].x); acc[rc * 4 + 1].y = fmaf(w.y, xv.y, acc[rc * 4 + 1].y);
+          acc[rc * 4 + 2].x = fmaf(w.z, xv.x, acc[rc * 4 + 2].x); acc[rc * 4 + 2].y = fmaf(w.z, xv.y, acc[rc * 4 + 2].y);
+          acc[rc * 4 + 3].x = fmaf(w.w, xv.x, acc[rc * 4 + 3].x); acc[rc * 4 + 3].y = fmaf(w.w, xv.y, acc[rc * 4 + 3].y);
+        }
+      }
+      if (more) {
+        const int k = k0 + G * GS + g * GS;
+        const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j)
+    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+}
+
 __device__ __forceinline__ float red_sum(const float* red, int j, int m) {
   float s = red[(0 * PIX_MAXROWS + j) * PIX_MB + m];
 #pragma unroll
@@ -439,7 +594,7 @@ __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixA
   p.a = 0.f; p.b = 0.f; p.valid = false;
   const int tid = threadIdx.x, m = tid & (PIX_MB - 1), j = tid >> 6;
   const PixLayout& a = A.lay;
-  if (t.epi == EPI_HGATE) {
+  if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
     if (j < (t.nrows >> 1) && (t.nrows >> 1) * PIX_MB <= PIX_THREADS) {
       const int q = (t.row0 >> 1) + j;
       const float* v2h = A.arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
@@ -447,12 +602,12 @@ __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixA
       p.b = __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
       p.valid = true;
     }
-  } else if (t.epi == EPI_HRES && t.layer > 0) {
+  } else if (t.epi == EPI_HRES && t.layer > 0 && !A.fused) {   // fused plan: x_h[l] is written by the previous stage
     if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
       p.a = __ldcg(A.arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + (t.row0 + j) * PIX_MB + m);
       p.valid = true;
     }
-  } else if (t.epi == EPI_FUSEH) {
+  } else if (t.epi == EPI_FUSEH || t.epi == EPI_HRESF) {
     if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
       p.a = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + t.row0 + j] : 0.f;
       p.valid = true;
@@ -461,6 +616,7 @@ __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixA
   return p;
 }
 
+template <int PIPE>
 __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, const EpiPre& pre) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PixLayout& a = A.lay;
@@ -468,19 +624,28 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
   const float* bias = Wsm + (size_t)t.K * t.rpad;
   float* arena = A.arena;
   for (int pass = 0; pass < npass; ++pass) {
-    int s_seg[6];
+    int s_seg[6];  // at most 6 segments (EPI_VERT0)
     resolve_segments(t, pass, r, a, A.L, s_seg);
     if (pass > 0) __syncthreads();  // previous pass's epilogue finished reading red
     if (t.K > 0) {
-      switch (t.rpad >> 2) {
-        case 1: mm_rows<1>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-        case 2: mm_rows<2>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-        case 3: mm_rows<3>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-        default: mm_rows<4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+      if constexpr (PIPE > 0) {
+        switch (t.rpad >> 2) {
+          case 1: mm_rows_pipe<1, PIPE>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 2: mm_rows_pipe<2, PIPE>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 3: mm_rows_pipe<3, PIPE>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          default: mm_rows_pipe<4, PIPE>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        }
+      } else {
+        switch (t.rpad >> 2) {
+          case 1: mm_rows<1>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 2: mm_rows<2>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 3: mm_rows<3>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          default: mm_rows<4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        }
       }
     }
     __syncthreads();
-    const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE);
+    const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE || t.epi == EPI_HGATE2);
     const int items = (pairs ? t.nrows >> 1 : t.nrows) * PIX_MB;
     for (int it = tid; it < items; it += PIX_THREADS) {
       const int m = it & (PIX_MB - 1), j = it >> 6;
@@ -490,13 +655,13 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
         float as = (t.K > 0 ? red_sum(red, 2 * j + 1, m) : 0.f) + bias[2 * j + 1];
         const float* cls = arena + a.CLS + (t.layer * 2) * PIX_SEG;
         float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
-        if (t.epi == EPI_HGATE) {
+        if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
           const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
           float vt = pre.valid ? pre.a : __ldcg(v2h + q * PIX_MB + m);
           float vs = pre.valid ? pre.b : __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
           float zt = (vt + at) + ct;
           float zs = (vs + as) + cs;
-          arena[a.G + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+          arena[a.G + (t.layer & 1) * PIX_SEG + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
         } else {
           float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
           hv[q * PIX_MB + m] = at;
@@ -522,11 +687,11 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
               arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
             }
             break;
-          case EPI_FUSEH: {
+          case EPI_FUSEH: case EPI_HRESF: {
             float au = pre.valid ? pre.a : (m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f);
             arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
           } break;
-          case EPI_OUT1: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
+          case EPI_OUT1: case EPI_OUT1F: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
           case EPI_OUT2: arena[a.LOG + ch * PIX_MB + m] = v; break;
         }
       }
@@ -605,16 +770,27 @@ __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m
   if (r >= A.T0 && tid == 0) A.idx_out[((size_t)m * (A.Ttot - A.T0) + (r - A.T0)) * 2 + c] = code;
   // embedding gather into the ring slot of this row (x_v = x_h = embedding(code) at layer 0)
   A.arena[A.lay.E + ((r & 3) * 2 + c) * PIX_SEG + tid * PIX_MB + m] = A.emb[(size_t)code * PIX_D + tid];
+  if (t.K) {
+    // fused plan: layer-0 gate of column 1 (its matmul input is embedding[code] only -> gathered from T0)
+    const float2 tw = *reinterpret_cast<const float2*>(A.blob + t.wofs + (size_t)code * (2 * PIX_D) + 2 * tid);
+    const float* v2h = A.arena + A.lay.V2H + ((0 * 2 + 1) * 2) * PIX_SEG;
+    const float* cls = A.arena + A.lay.CLS;
+    const float zt = (__ldcg(v2h + tid * PIX_MB + m) + tw.x) + cls[tid * PIX_MB + m];
+    const float zs = (__ldcg(v2h + (PIX_D + tid) * PIX_MB + m) + tw.y) + cls[(PIX_D + tid) * PIX_MB + m];
+    A.arena[A.lay.G + tid * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+  }
 }
 
-constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB) * sizeof(float) + 64;
+constexpr int PIX_MAXSTAGES = 160;  // this CTA's column of the stage table is kept in shared memory
+constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB) * sizeof(float) + 64 + PIX_MAXSTAGES * sizeof(PixTask);
 
-template <bool PERSISTENT>
+template <bool PERSISTENT, int PIPE>
 __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int r_single, int s_single) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* wbuf = reinterpret_cast<float*>(smem_raw);
   float* red = wbuf + 2 * PIX_WBUF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * PIX_MAXROWS * PIX_MB);
+  PixTask* tasks = reinterpret_cast<PixTask*>(bars + 8);
   const int tid = threadIdx.x, cta = blockIdx.x;
 
   if (!PERSISTENT) {
@@ -626,7 +802,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     for (int i = tid; i < nf; i += PIX_THREADS) wbuf[i] = A.blob[t.wofs + i];
     __syncthreads();
     EpiPre pre; pre.a = pre.b = 0.f; pre.valid = false;
-    run_matmul_task(t, A, r_single, wbuf, red, pre);
+    run_matmul_task<0>(t, A, r_single, wbuf, red, pre);
     return;
   }
 
@@ -635,12 +811,14 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < A.nstages * 8; i += PIX_THREADS)
+    reinterpret_cast<int*>(tasks)[i] = reinterpret_cast<const int*>(A.table + (size_t)(i >> 3) * A.ncta + cta)[i & 7];
   __syncthreads();
   uint32_t uses[2] = {0u, 0u};
   const int total = A.Ttot * A.nstages;
   // prefetch the first task's weights
   if (tid == 0) {
-    const PixTask t0 = A.table[cta];
+    const PixTask t0 = tasks[0];
     if (task_active(t0, 0, A.log_r0) && t0.epi != EPI_SAMPLE) {
       mbar_expect_tx(&bars[0], task_bytes(t0));
       tma_load_1d(wbuf, A.blob + t0.wofs, task_bytes(t0), &bars[0]);
@@ -648,14 +826,14 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
   }
   int r = 0, s = 0;
   for (int g = 0; g < total; ++g) {
-    const PixTask t = A.table[(size_t)s * A.ncta + cta];
+    const PixTask t = tasks[s];
     const int buf = g & 1;
     // prefetch next stage's weight slice into the other buffer (its last reader finished before the
     // __syncthreads of the previous grid_arrive)
     if (tid == 0 && g + 1 < total) {
       int s1 = s + 1, r1 = r;
       if (s1 == A.nstages) { s1 = 0; r1 = r + 1; }
-      const PixTask tn = A.table[(size_t)s1 * A.ncta + cta];
+      const PixTask tn = tasks[s1];
       if (task_active(tn, r1, A.log_r0) && tn.epi != EPI_SAMPLE) {
         fence_proxy_async();
         mbar_expect_tx(&bars[buf ^ 1], task_bytes(tn));
@@ -671,7 +849,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);  // every CTA finished stage g-1
     if (active) {
       if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
-      else run_matmul_task(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
+      else run_matmul_task<PIPE>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
     grid_arrive(A.barrier);
     if (++s == A.nstages) { s = 0; ++r; }
@@ -786,20 +964,23 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   A.audv = audv; A.audh = audh; A.noise = noise; A.pre = pre; A.idx_out = idx_out; A.logits_out = logits_out;
   A.barrier = P->d_barrier; A.lay = P->lay;
   A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
+  A.fused = P->fused ? 1 : 0;
   (void)noise_B;
   if (e->pixel_mode == 0) {
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
+    static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 4;   // A/B switch: load-ring depth in groups of 8 rows (0: burst loads)
+    void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : (void*)pixelcnn_kernel<true, 4>;
+    TS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
     if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
-    TS_CUDA(cudaLaunchCooperativeKernel((void*)pixelcnn_kernel<true>, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
+    TS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
     if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
     e->launches++;
   } else {
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     for (int r = 0; r < Ttot; ++r)
       for (int st = 0; st < P->nstages; ++st) {
-        pixelcnn_kernel<false><<<P->ncta, PIX_THREADS, PIX_SMEM, s>>>(A, r, st);
+        pixelcnn_kernel<false, 0><<<P->ncta, PIX_THREADS, PIX_SMEM, s>>>(A, r, st);
         e->launches++;
       }
     TS_CUDA(cudaGetLastError());
@@ -821,7 +1002,7 @@ using namespace ts;
 extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
-  PixelPlan* P = build_plan(e, ck);
+  PixelPlan* P = build_plan(e, ck, e->pixel_fusion);
   P->p2 = build_plan2(e, ck, P->L);
   delete e->pix;
   e->pix = P;

@@ -24,7 +24,11 @@ enum PixEpi {
   EPI_FUSEH = 7,   // fusion_h (x_h half)
   EPI_OUT1 = 8,    // output_conv.0 + ReLU
   EPI_OUT2 = 9,    // output_conv.2 -> logits
-  EPI_SAMPLE = 10  // softmax + categorical draw + embedding gather
+  EPI_SAMPLE = 10, // softmax + categorical draw + embedding gather (K = 1: also emits layer-0 G of column 1)
+  // fused plan (52 stages): linear stages folded into the gate matmul that consumes them
+  EPI_HRESF = 11,  // (fusion_h . horiz_resid_0) G_0 + audio term -> x_h[1]
+  EPI_HGATE2 = 12, // gate of layer l on (horiz_stack_l . horiz_resid_{l-1}) G_{l-1} + horiz_stack_l x_h[l-1] (+ column-0 tap)
+  EPI_OUT1F = 13   // output_conv.0 on (W horiz_resid_{L-1}) G_{L-1} + W x_h[L-1], ReLU
 };
 
 struct PixTask {  // one CTA's work in one stage (8 ints)
@@ -37,6 +41,7 @@ struct PixLayout {  // arena offsets in floats
 
 struct PixelPlan {
   int L = 0, ncta = 0, nstages = 0, nclasses = 4;
+  bool fused = false;          // 52-stage plan (EPI_HRESF / EPI_HGATE2 / EPI_OUT1F), else the plain 84-stage plan
   PixLayout lay;
   std::vector<PixTask> table;  // [nstages][ncta]
   std::vector<float> blob;     // packed per-task weights: [K][rpad] then bias [rpad]

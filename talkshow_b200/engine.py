@@ -75,6 +75,10 @@ class Engine:
     def set_tensor_cores(self, enable=True):
         self._check(self.L.ts_set_tensor_cores(self.h, int(enable)), "ts_set_tensor_cores")
 
+    def set_pixelcnn_fusion(self, on):
+        """Plan built by the next load_pixelcnn: fused 52-stage (default) or plain 84-stage."""
+        self._check(self.L.ts_set_pixelcnn_fusion(self.h, int(bool(on))), "ts_set_pixelcnn_fusion")
+
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
 

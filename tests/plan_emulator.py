@@ -6,7 +6,8 @@ and the schedule can be validated against the oracle on a machine without a GPU.
 """
 import numpy as np
 
-EPI_IDLE, EPI_VERT0, EPI_VERT, EPI_V2H, EPI_FUSEV, EPI_HGATE, EPI_HRES, EPI_FUSEH, EPI_OUT1, EPI_OUT2, EPI_SAMPLE = range(11)
+(EPI_IDLE, EPI_VERT0, EPI_VERT, EPI_V2H, EPI_FUSEV, EPI_HGATE, EPI_HRES, EPI_FUSEH, EPI_OUT1, EPI_OUT2, EPI_SAMPLE,
+ EPI_HRESF, EPI_HGATE2, EPI_OUT1F) = range(14)
 D, MB, SEG = 256, 64, 256 * 64
 
 
@@ -44,7 +45,16 @@ def segments(t, pas, r, lay, L):
             s.append(lay["XH"] + (1 * (L + 1) + layer) * SEG)
         return s
     if epi == EPI_HRES:
+        return [lay["G"] + (layer & 1) * SEG]
+    if epi == EPI_HRESF:
         return [lay["G"]]
+    if epi == EPI_HGATE2:
+        s = [lay["G"] + ((layer - 1) & 1) * SEG, lay["XH"] + (col * (L + 1) + layer - 1) * SEG]
+        if col == 1:
+            s.append(lay["XH"] + (0 * (L + 1) + layer) * SEG)
+        return s
+    if epi == EPI_OUT1F:
+        return [lay["G"] + ((L - 1) & 1) * SEG, lay["XH"] + (col * (L + 1) + L - 1) * SEG]
     if epi == EPI_FUSEH:
         return [lay["XHP"]]
     if epi == EPI_OUT1:
@@ -89,6 +99,12 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                         code = int(np.argmax(p / noise[2 * (r - T0) + col, m]))
                     codes[m, r, col] = code
                     writes.append((lay["E"] + ((r & 3) * 2 + col) * SEG, m, emb[code]))
+                    if K:   # fused plan: layer-0 gate of column 1 gathered from the code table T0 [2048][512]
+                        tw = plan.blob[wofs + code * 2 * D: wofs + (code + 1) * 2 * D]
+                        v2h = A(lay["V2H"] + ((0 * 2 + 1) * 2) * SEG, 2 * SEG)
+                        zt = (v2h[:D, m] + tw[0::2]) + cls[0][:D, m]
+                        zs = (v2h[D:, m] + tw[1::2]) + cls[0][D:, m]
+                        writes.append((lay["G"], m, np.tanh(zt) * _sigmoid(zs)))
                     continue
                 W = plan.blob[wofs:wofs + K * rpad].reshape(K, rpad)[:, :nrows]
                 bias = plan.blob[wofs + K * rpad: wofs + K * rpad + nrows]
@@ -102,15 +118,15 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                     else:
                         acc = np.zeros((nrows, MB), np.float32)
                     acc = acc + bias[:, None]
-                    if epi in (EPI_VERT0, EPI_VERT, EPI_HGATE):
+                    if epi in (EPI_VERT0, EPI_VERT, EPI_HGATE, EPI_HGATE2):
                         q0, nq = row0 // 2, nrows // 2
                         at, as_ = acc[0::2], acc[1::2]
                         ct, cs = cls[layer][q0:q0 + nq], cls[layer][D + q0:D + q0 + nq]
-                        if epi == EPI_HGATE:
+                        if epi in (EPI_HGATE, EPI_HGATE2):
                             v2h = A(lay["V2H"] + ((layer * 2 + col) * 2) * SEG, 2 * SEG)
                             zt = (v2h[q0:q0 + nq] + at) + ct
                             zs = (v2h[D + q0:D + q0 + nq] + as_) + cs
-                            writes.append((lay["G"], (q0, nq), np.tanh(zt) * _sigmoid(zs)))
+                            writes.append((lay["G"] + (layer & 1) * SEG, (q0, nq), np.tanh(zt) * _sigmoid(zs)))
                         else:
                             hvo = lay["HV"] + (((layer & 1) * 2 + col) * 2) * SEG
                             writes.append((hvo, (q0, nq), at.copy()))
@@ -134,11 +150,11 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                             else:
                                 xh = A(lay["XH"] + (col * (L + 1) + layer) * SEG)[row0:row0 + nrows]
                                 writes.append((lay["XH"] + (col * (L + 1) + layer + 1) * SEG, sl, acc + xh))
-                        elif epi == EPI_FUSEH:
+                        elif epi in (EPI_FUSEH, EPI_HRESF):
                             au = np.zeros((nrows, MB), np.float32)
                             au[:, :B] = audh[:, r, row0:row0 + nrows].T
                             writes.append((lay["XH"] + (col * (L + 1) + 1) * SEG, sl, acc + au))
-                        elif epi == EPI_OUT1:
+                        elif epi in (EPI_OUT1, EPI_OUT1F):
                             writes.append((lay["Y"], sl, np.maximum(acc, 0)))
                         elif epi == EPI_OUT2:
                             writes.append((lay["LOG"], sl, acc))

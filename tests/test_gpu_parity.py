@@ -142,6 +142,33 @@ def test_pixelcnn_generate_b3_t75(eng, ckpts):
         assert np.abs(poses.cpu().numpy()[:, ::int(gold["pred_stride"])] - gold["pred"]).max() <= TOL
 
 
+def test_pixelcnn_plain_plan(eng, ckpts):
+    """The plain 84-stage plan (one stage per reference conv, ts_set_pixelcnn_fusion(0)) and the default fused
+    52-stage plan sample the same sequences as the oracle; their logits agree within fp32 rounding order."""
+    from talkshow_b200.engine import Engine
+
+    e = Engine(0)
+    e.set_pixelcnn_fusion(False)
+    e.load_pixelcnn(ckpts["pixel"]["generator"])
+    try:
+        B, T = 5, 20
+        label = torch.tensor([0, 1, 2, 3, 1])
+        aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], synth.synth_mfcc(B, 4 * T, seed=41))
+        noise = draw_noise(2 * T, B, 17)
+        ref = O.pixelcnn_generate(ckpts["pixel"]["generator"], label, T, B, aud.unsqueeze(-1).repeat(1, 1, 1, 2),
+                                  noise=noise, window=18)
+        plain, lp = e.pixelcnn_generate(aud, label, noise, want_logits=True)
+        fused, lf = eng.pixelcnn_generate(aud, label, noise, want_logits=True)
+        assert torch.equal(plain.cpu(), ref)
+        assert torch.equal(fused.cpu(), ref)
+        d = (lp - lf).abs().max().item()
+        print("fused vs plain plan logits max-abs diff: %.3e" % d)
+        assert d <= TOL
+    finally:
+        torch.cuda.synchronize()
+        e.close()
+
+
 def test_pixelcnn_continuity(eng, ckpts):
     """generate(pre_latents, pre_audio), gated_pixelcnn_v2.py:158-165."""
     gold = _load("pixel_cont")
