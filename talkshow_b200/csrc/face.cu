@@ -323,8 +323,182 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   }
 }
 
+// ---- tensor-core attention (legacy warp-level MMA, 3xTF32) -------------------------------------------
+// One CTA per (batch, head): K and V of the head live in shared memory as fp32 (row stride 68 floats, which
+// makes both fragment access patterns below bank-conflict free); every warp owns 16-query row blocks and runs
+// an online-softmax pass over 64-key blocks with mma.sync.m16n8k8 (tf32 inputs, fp32 accumulate).  fp32 accuracy
+// comes from the 3xTF32 split x = hi + lo (both rounded to tf32 with cvt.rna; products lo*hi + hi*lo + hi*hi),
+// done in registers: Q once per row block, K / V / P on the fly.  The P accumulator fragment is fed to the PV
+// product without shuffles by letting MMA k-slot t / t+4 stand for keys 2t / 2t+1 of the 8-key step (a
+// permutation of the reduction index applied to both operands).
+constexpr int ATT_LD = 68;
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 3xTF32 products of one A fragment (hi, lo) against four B fragments, small terms first; the four
+// accumulators are independent, so each pass keeps four MMAs in flight per warp
+__device__ __forceinline__ void mma3x4(float (&c0)[4], float (&c1)[4], float (&c2)[4], float (&c3)[4], const uint32_t (&ah)[4],
+                                       const uint32_t (&al)[4], const float (&bf)[8]) {
+  uint32_t bh[8], bl[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_tf32(bf[i], bh[i], bl[i]);
+  mma_tf32(c0, al, bh[0], bh[1]); mma_tf32(c1, al, bh[2], bh[3]); mma_tf32(c2, al, bh[4], bh[5]); mma_tf32(c3, al, bh[6], bh[7]);
+  mma_tf32(c0, ah, bl[0], bl[1]); mma_tf32(c1, ah, bl[2], bl[3]); mma_tf32(c2, ah, bl[4], bl[5]); mma_tf32(c3, ah, bl[6], bl[7]);
+  mma_tf32(c0, ah, bh[0], bh[1]); mma_tf32(c1, ah, bh[2], bh[3]); mma_tf32(c2, ah, bh[4], bh[5]); mma_tf32(c3, ah, bh[6], bh[7]);
+}
+
+constexpr int ATT_WARPS = 10;
+__global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                          float* __restrict__ out_lo, int T, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int Tp = (T + 63) & ~63;      // keys padded to whole 64-key blocks (pad rows are zero and masked)
+  float* Ks = sm;                     // [Tp][ATT_LD]
+  float* Vs = sm + (size_t)Tp * ATT_LD;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ld = 3 * H * 64;
+  const float* base = qkv + (size_t)b * T * ld + h * 64;
+  for (int i = tid; i < Tp * 16; i += ATT_WARPS * 32) {
+    const int r = i >> 4, c4 = (i & 15) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < T) {
+      kv = *reinterpret_cast<const float4*>(base + (size_t)r * ld + H * 64 + c4);
+      vv = *reinterpret_cast<const float4*>(base + (size_t)r * ld + 2 * H * 64 + c4);
+    }
+    *reinterpret_cast<float4*>(Ks + r * ATT_LD + c4) = kv;
+    *reinterpret_cast<float4*>(Vs + r * ATT_LD + c4) = vv;
+  }
+  __syncthreads();
+  const int nrb = (T + 15) >> 4;
+  for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
+    const int ra = rb * 16 + g, rbw = ra + 8;     // the two query rows this thread holds fragments of
+    uint32_t qh[8][4], ql[8][4];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const float* qa = base + (size_t)ra * ld + ks * 8 + t;
+      const float* qb = base + (size_t)rbw * ld + ks * 8 + t;
+      const float a0 = ra < T ? qa[0] * scale : 0.f, a2 = ra < T ? qa[4] * scale : 0.f;
+      const float a1 = rbw < T ? qb[0] * scale : 0.f, a3 = rbw < T ? qb[4] * scale : 0.f;
+      split_tf32(a0, qh[ks][0], ql[ks][0]);
+      split_tf32(a1, qh[ks][1], ql[ks][1]);
+      split_tf32(a2, qh[ks][2], ql[ks][2]);
+      split_tf32(a3, qh[ks][3], ql[ks][3]);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+    for (int kb = 0; kb < Tp; kb += 64) {
+      float sc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      // S = Q K^T:  B fragment (k = d, n = key): b0 = K[key = kb + 8 nt + g][8 ks + t], b1 = ...[8 ks + t + 4]
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+        for (int n4 = 0; n4 < 8; n4 += 4) {
+          const float* kr = Ks + (kb + n4 * 8 + g) * ATT_LD + ks * 8 + t;
+          float bf[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { bf[2 * i] = kr[i * 8 * ATT_LD]; bf[2 * i + 1] = kr[i * 8 * ATT_LD + 4]; }
+          mma3x4(sc[n4], sc[n4 + 1], sc[n4 + 2], sc[n4 + 3], qh[ks], ql[ks], bf);
+        }
+      }
+      // mask the padded keys, block row maxima (accumulator columns: keys kb + 8 nt + 2t, +1; rows g / g+8)
+      float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = kb + nt * 8 + 2 * t;
+        if (key >= T) sc[nt][0] = sc[nt][2] = -INFINITY;
+        if (key + 1 >= T) sc[nt][1] = sc[nt][3] = -INFINITY;
+        mx_a = fmaxf(mx_a, fmaxf(sc[nt][0], sc[nt][1]));
+        mx_b = fmaxf(mx_b, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+      const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);   // finite: every key block holds a valid key
+      const float ca = expf(m_a - mn_a), cb = expf(m_b - mn_b);
+      m_a = mn_a; m_b = mn_b;
+      l_a *= ca; l_b *= cb;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= ca; o[dt][1] *= ca; o[dt][2] *= cb; o[dt][3] *= cb; }
+      // O += P V:  A fragment of key step j = accumulator fragment of n-tile j (slot t <-> key 2t, slot t+4 <-> key 2t+1);
+      // B fragment (k-slot, n = d): b0 = V[kb + 8 j + 2t][8 dt + g], b1 = V[kb + 8 j + 2t + 1][8 dt + g]
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kb + j * 8 >= T) break;       // whole 8-key step is padding (warp-uniform)
+        const float p0 = expf(sc[j][0] - mn_a), p1 = expf(sc[j][1] - mn_a);
+        const float p2 = expf(sc[j][2] - mn_b), p3 = expf(sc[j][3] - mn_b);
+        l_a += p0 + p1;
+        l_b += p2 + p3;
+        uint32_t ph[4], pl[4];
+        split_tf32(p0, ph[0], pl[0]);   // a0: row g,   slot t
+        split_tf32(p2, ph[1], pl[1]);   // a1: row g+8, slot t
+        split_tf32(p1, ph[2], pl[2]);   // a2: row g,   slot t+4
+        split_tf32(p3, ph[3], pl[3]);   // a3: row g+8, slot t+4
+        const float* vr = Vs + (kb + j * 8 + 2 * t) * ATT_LD + g;
+#pragma unroll
+        for (int d4 = 0; d4 < 8; d4 += 4) {
+          float bf[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { bf[2 * i] = vr[(d4 + i) * 8]; bf[2 * i + 1] = vr[ATT_LD + (d4 + i) * 8]; }
+          mma3x4(o[d4], o[d4 + 1], o[d4 + 2], o[d4 + 3], ph, pl, bf);
+        }
+      }
+    }
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+    const float ia = 1.0f / l_a, ib = 1.0f / l_b;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = half ? rbw : ra;
+        if (row >= T) continue;
+        const float inv = half ? ib : ia;
+        const float v0 = o[dt][half * 2] * inv, v1 = o[dt][half * 2 + 1] * inv;
+        const size_t at = ((size_t)b * T + row) * (H * 64) + h * 64 + dt * 8 + 2 * t;
+        if (out_lo) {
+          const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+          *reinterpret_cast<float2*>(out + at) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(out_lo + at) = make_float2(v0 - h0, v1 - h1);
+        } else {
+          *reinterpret_cast<float2*>(out + at) = make_float2(v0, v1);
+        }
+      }
+    }
+  }
+}
+
 static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
+  {
+    static const bool use_mma = !(getenv("TS_ATT_MMA") && atoi(getenv("TS_ATT_MMA")) == 0);   // A/B switch
+    const int Tp64 = (T + 63) & ~63;
+    const size_t smem_mma = (size_t)2 * Tp64 * ATT_LD * sizeof(float);
+    if (use_mma && smem_mma <= 220 * 1024) {
+      TS_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+      attention_mma_kernel<<<B * H, ATT_WARPS * 32, smem_mma, s>>>(qkv, out, out_lo, T, H, 0.125f);
+      e->launches++;
+      TS_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const int Tp = (T + 63) & ~63;
   auto smem = [&](int QT) { return (size_t)(QT * 65 + 64 * 65 + QT * Tp) * sizeof(float); };
   const float scale = 0.125f;  // head_dim ** -0.5

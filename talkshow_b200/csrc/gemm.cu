@@ -12,6 +12,19 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
+// Blackwell packed fp32 FMA (SASS FFMA2): two IEEE fp32 FMAs per lane per instruction, bit-identical to two
+// fmaf.  acc / b hold two adjacent output columns, the A element is the broadcast operand.
+__device__ __forceinline__ void fma2(unsigned long long& acc, float a, unsigned long long b) {
+  unsigned long long aa;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(b));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p) {
   constexpr int BK = 16;
@@ -87,11 +100,11 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
   };
 
   const int ty = tid / (BN / TN), tx = tid % (BN / TN);
-  float acc[TM][TN];
+  unsigned long long acc2[TM][TN / 2];   // column pairs (j, j+1)
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc2[i][j] = 0ull;
 
   gload(0);
   sstore(0);
@@ -102,7 +115,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
     if (more) gload(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[TM], b[TN];
+      float a[TM];
+      unsigned long long b2[TN / 2];
 #pragma unroll
       for (int i = 0; i < TM; i += 4) {
         float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][ty * TM + i]);
@@ -110,13 +124,13 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
       }
 #pragma unroll
       for (int j = 0; j < TN; j += 4) {
-        float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * TN + j]);
-        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+        ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&Bs[buf][kk][tx * TN + j]);
+        b2[j / 2] = v.x; b2[j / 2 + 1] = v.y;
       }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) fma2(acc2[i][j], a[i], b2[j]);
     }
     if (more) sstore(buf ^ 1);
     __syncthreads();
@@ -142,11 +156,13 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
     for (int j = 0; j < TN; j += 4) {
       int n = n0 + tx * TN + j;
       if (n >= p.N) continue;
+      const float2 c01 = unpack2(acc2[i][j / 2]), c23 = unpack2(acc2[i][j / 2 + 1]);
+      const float accq[4] = {c01.x, c01.y, c23.x, c23.y};
       float v[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         int nn = n + q;
-        float x = acc[i][j + q];
+        float x = accq[q];
         if (nn < p.N) {
           if (bias) x += bias[nn];
           if (rrow) x += rrow_lo ? (rrow[nn] + rrow_lo[nn]) : rrow[nn];
