@@ -111,6 +111,10 @@ int ts_mfcc_frames(int N, int sr);
 int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* out, int B, int Ff, int Fb,
                      int stand, void* stream);
 
+/* scripts/demo.py:185-188,216-219 (convert_to_6d configs): matrix_to_axis_angle(rotation_6d_to_matrix(x)),
+ * data_utils/rotation_conversion.py:512-533,433-447.  d6 [n,6] -> aa [n,3] (device pointers). */
+int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, int64_t n, void* stream);
+
 /* ---- introspection (tests / bench) ---------------------------------------------------------- */
 /* number of kernel launches issued by this engine since creation */
 int64_t ts_launch_count(ts_engine* e);

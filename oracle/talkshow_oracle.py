@@ -371,6 +371,37 @@ def assemble_pose(face, body, stand=False):
     return part2full(torch.cat([jaw, body, exp], -1), stand)
 
 
+def rot6d_to_axis_angle(d6):
+    """matrix_to_axis_angle(rotation_6d_to_matrix(d6)) restated: data_utils/rotation_conversion.py:512-533
+    (Gram-Schmidt), :98-118 (matrix_to_quaternion with _sqrt_positive_part / _copysign), :481-507
+    (quaternion_to_axis_angle, small-angle branch at 1e-6).  d6 [...,6] -> [...,3]."""
+    a1, a2 = d6[..., :3], d6[..., 3:]
+    b1 = F.normalize(a1, dim=-1)
+    b2 = a2 - (b1 * a2).sum(-1, keepdim=True) * b1
+    b2 = F.normalize(b2, dim=-1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    m = torch.stack((b1, b2, b3), dim=-2)
+    m00, m11, m22 = m[..., 0, 0], m[..., 1, 1], m[..., 2, 2]
+
+    def sqp(x):
+        return torch.where(x > 0, torch.sqrt(x.clamp_min(0)), torch.zeros_like(x))
+
+    def cps(a, b):
+        return torch.where((a < 0) != (b < 0), -a, a)
+
+    q0 = 0.5 * sqp(1 + m00 + m11 + m22)
+    q1 = cps(0.5 * sqp(1 + m00 - m11 - m22), m[..., 2, 1] - m[..., 1, 2])
+    q2 = cps(0.5 * sqp(1 - m00 + m11 - m22), m[..., 0, 2] - m[..., 2, 0])
+    q3 = cps(0.5 * sqp(1 - m00 - m11 + m22), m[..., 1, 0] - m[..., 0, 1])
+    v = torch.stack((q1, q2, q3), -1)
+    norms = torch.norm(v, p=2, dim=-1, keepdim=True)
+    half = torch.atan2(norms, q0.unsqueeze(-1))
+    ang = 2 * half
+    small = ang.abs() < 1e-6
+    s = torch.where(small, 0.5 - ang * ang / 48, torch.sin(half) / torch.where(small, torch.ones_like(ang), ang))
+    return v / s
+
+
 def latent_rows(n_mfcc_frames):
     """T for M MFCC frames: two k4/s2/p1 downsamples (vqvae_modules.py:105-106)."""
     m = (n_mfcc_frames + 2 - 4) // 2 + 1

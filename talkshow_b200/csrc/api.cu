@@ -130,6 +130,51 @@ extern "C" int ts_assemble_pose(ts_engine* e, const float* face, const float* bo
   TS_API_END(e)
 }
 
+// ---- 6-D rotation -> axis-angle: matrix_to_axis_angle(rotation_6d_to_matrix(x)) ----------------------
+// (data_utils/rotation_conversion.py:512-533 Gram-Schmidt, :98-118 matrix_to_quaternion, :481-507
+// quaternion_to_axis_angle; applied by scripts/demo.py:185-188,216-219 when convert_to_6d is set)
+__global__ void rot6d_to_aa_kernel(const float* __restrict__ d6, float* __restrict__ aa, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float* p = d6 + i * 6;
+    const float a1x = p[0], a1y = p[1], a1z = p[2], a2x = p[3], a2y = p[4], a2z = p[5];
+    float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);           // F.normalize eps
+    const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+    const float d = b1x * a2x + b1y * a2y + b1z * a2z;
+    float b2x = a2x - d * b1x, b2y = a2y - d * b1y, b2z = a2z - d * b1z;
+    float n2 = fmaxf(sqrtf(b2x * b2x + b2y * b2y + b2z * b2z), 1e-12f);
+    b2x /= n2; b2y /= n2; b2z /= n2;
+    const float b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
+    // rows of the matrix are b1, b2, b3
+    const float m00 = b1x, m11 = b2y, m22 = b3z;
+    auto sqp = [](float v) { return v > 0.f ? sqrtf(v) : 0.f; };                     // _sqrt_positive_part
+    const float q0 = 0.5f * sqp(1.f + m00 + m11 + m22);
+    float q1 = 0.5f * sqp(1.f + m00 - m11 - m22);
+    float q2 = 0.5f * sqp(1.f - m00 + m11 - m22);
+    float q3 = 0.5f * sqp(1.f - m00 - m11 + m22);
+    if (b3y - b2z < 0.f) q1 = -q1;        // _copysign(x, m21 - m12)
+    if (b1z - b3x < 0.f) q2 = -q2;        // _copysign(y, m02 - m20)
+    if (b2x - b1y < 0.f) q3 = -q3;        // _copysign(z, m10 - m01)
+    const float nv = sqrtf(q1 * q1 + q2 * q2 + q3 * q3);
+    const float half = atan2f(nv, q0), ang = 2.f * half;
+    const float sh = fabsf(ang) < 1e-6f ? 0.5f - (ang * ang) / 48.f : sinf(half) / ang;
+    aa[i * 3 + 0] = q1 / sh;
+    aa[i * 3 + 1] = q2 / sh;
+    aa[i * 3 + 2] = q3 / sh;
+  }
+}
+
+extern "C" int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, int64_t n, void* stream) {
+  TS_API_BEGIN(e)
+  if (n < 0) fail(TS_ERR_INVALID, "ts_rot6d_to_axis_angle: n=%lld", (long long)n);
+  if (n > 0) {
+    int blocks = (int)std::min<long>((n + 255) / 256, 148 * 8);
+    rot6d_to_aa_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d6, aa, (long)n);
+    e->launches++;
+    TS_CUDA(cudaGetLastError());
+  }
+  TS_API_END(e)
+}
+
 // ---- fused body path: audio encoder -> PixelCNN sampler -> two VQ decoders -------------------------
 extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise,
                                 int64_t* codes, float* poses, int B, int M, void* stream) {

@@ -235,6 +235,10 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
   PixelPlan* P = new PixelPlan();
   P->L = L;
   P->ncta = e->sm_count;
+  if (const char* v = getenv("TS_PIX_CTAS")) {   // experiment switch: persistent CTAs (every CTA re-reads the stage's activations from L2)
+    const int n = atoi(v);
+    if (n >= PIX_MB && n <= e->sm_count) P->ncta = n;
+  }
   P->nclasses = ncls;
   P->lay = make_layout(L);
   if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);

@@ -10,7 +10,7 @@ constexpr int PIX_MB = 64;      // batch tile: every activation row is [channel]
 constexpr int PIX_SEG = PIX_D * PIX_MB;  // floats in one [256][64] activation segment
 constexpr int PIX_THREADS = 256;
 constexpr int PIX_MAXROWS = 16; // weight rows one CTA handles per stage
-constexpr int PIX_WBUF = 12800; // floats per weight staging buffer (51.2 KB), two buffers
+constexpr int PIX_WBUF = 18560; // floats per weight staging buffer (74.2 KB), two buffers
 constexpr int PIX_NCODE = 2048;
 
 enum PixEpi {

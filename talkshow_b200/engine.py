@@ -228,6 +228,16 @@ class Engine:
                 "ts_body_generate")
         return codes, poses
 
+    def rot6d_to_axis_angle(self, d6):
+        """matrix_to_axis_angle(rotation_6d_to_matrix(d6)) (rotation_conversion.py:512-533,433-447): [...,6] -> [...,3]."""
+        d6 = self._dev(d6, torch.float32)
+        if d6.shape[-1] != 6:
+            raise ValueError("rot6d_to_axis_angle: last dim must be 6, got %s" % (tuple(d6.shape),))
+        out = torch.empty(d6.shape[:-1] + (3,), device=self.device)
+        self._check(self.L.ts_rot6d_to_axis_angle(self.h, _lib.ptr(d6), _lib.ptr(out), d6.numel() // 6, self._s()),
+                    "ts_rot6d_to_axis_angle")
+        return out
+
     def assemble_pose(self, face, body, stand=False):
         """demo.py:182-229 + part2full: face [B,Ff,103], body [B,Fb,129] -> [B,Ff,265]."""
         face = self._dev(face, torch.float32)

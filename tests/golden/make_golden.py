@@ -156,6 +156,21 @@ def main():
                             wave_head=wave[0, :64].numpy(),
                             fp=np.array(list(synth.fingerprint(face_ckpt).values())))
         print("face", o1.shape, float(np.abs(o1).max()), o2.shape)
+    # ---- 6-D rotation -> axis-angle (demo.py:185-188,216-219 for convert_to_6d configs) ----------
+    if want("rot6d"):
+        from data_utils.rotation_conversion import matrix_to_axis_angle, rotation_6d_to_matrix, axis_angle_to_matrix, matrix_to_rotation_6d
+        g = torch.Generator().manual_seed(23)
+        d6 = torch.randn(4096, 6, generator=g)
+        # edge cases: exact identity, tiny angles (small-angle branch), near-pi turns, unnormalised / nearly parallel inputs
+        aa = torch.randn(64, 3, generator=g)
+        aa = aa / aa.norm(dim=-1, keepdim=True)
+        ang = torch.cat([torch.zeros(8), torch.logspace(-9, -3, 24), 3.14159 - torch.logspace(-6, -1, 16), torch.full((16,), 1.0)])
+        special = matrix_to_rotation_6d(axis_angle_to_matrix(aa * ang[:, None]))
+        special[-16:] *= torch.logspace(-3, 3, 16)[:, None]                  # scale invariance of the Gram-Schmidt step
+        d6 = torch.cat([d6, special], 0)
+        out = matrix_to_axis_angle(rotation_6d_to_matrix(d6))
+        np.savez_compressed(os.path.join(HERE, "rot6d.npz"), d6=d6.numpy(), aa=out.numpy())
+        print("rot6d", d6.shape, float(out.abs().max()), bool(torch.isfinite(out).all()))
     os.chdir(cwd)
 
 

@@ -4,6 +4,7 @@ seeded inputs and against the reference-generated golden fixtures.
 Bars (BASELINE.json north_star): bit-exact VQ code indices (sampled sequences and argmin
 encodes); floating-point outputs within 1e-4 max-abs.
 """
+import math
 import os
 
 import numpy as np
@@ -265,3 +266,30 @@ def test_device_mfcc_matches_torchaudio(eng):
         err = np.abs(got - ref).max()
         print("device MFCC vs torchaudio (sr0=%d): max-abs %.3e (|ref| max %.1f)" % (sr0, err, np.abs(ref).max()))
         assert err <= 2e-2
+
+
+def test_rot6d_to_axis_angle(eng):
+    """SURVEY.md §8f-2 (convert_to_6d post-processing): ts_rot6d_to_axis_angle vs the reference-generated golden.
+    Away from a half turn the axis-angle vectors agree elementwise; within 0.1 rad of pi the representation is
+    ill-conditioned (the sign of the axis follows differences that vanish), so those rows are compared as
+    rotations (R(a) R(b)^T = I)."""
+    gold = _load("rot6d")
+    got = eng.rot6d_to_axis_angle(torch.tensor(gold["d6"])).cpu()
+    ref = torch.tensor(gold["aa"])
+    assert torch.isfinite(got).all()
+    ang = ref.norm(dim=-1)
+    ok = ang < math.pi - 0.1
+    assert ok.sum() > 4000
+    assert (got[ok] - ref[ok]).abs().max().item() <= 1e-4
+
+    def rotmat(a):      # Rodrigues in float64
+        a = a.double()
+        th = a.norm(dim=-1, keepdim=True).clamp_min(1e-30)
+        k = a / th
+        K = torch.zeros(a.shape[0], 3, 3, dtype=torch.float64)
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -k[:, 2], k[:, 1], k[:, 2], -k[:, 0], -k[:, 1], k[:, 0]
+        th = th[..., None]
+        return torch.eye(3, dtype=torch.float64) + torch.sin(th) * K + (1 - torch.cos(th)) * (K @ K)
+
+    d = rotmat(got[~ok]) @ rotmat(ref[~ok]).transpose(1, 2) - torch.eye(3, dtype=torch.float64)
+    assert d.abs().max().item() <= 1e-3

@@ -108,3 +108,12 @@ def test_pose_assembly_layout():
     assert torch.allclose(full[:, 9:12], torch.tensor([3.0747, -0.0158, -0.0152]).expand(5, 3))
     assert torch.equal(full[4, -100:], face[4, 3:])
     assert torch.equal(full[4, 3 + 15:3 + 18], body[3, :3])      # last body frame repeated
+
+
+def test_rot6d_to_axis_angle_golden():
+    """f2 piece: oracle restatement == the reference's matrix_to_axis_angle(rotation_6d_to_matrix(x)) run here
+    (tests/golden/make_golden.py --only rot6d): random inputs, identity, tiny angles, near-pi turns, scaled inputs."""
+    gold = np.load(os.path.join(GOLDEN, "rot6d.npz"))
+    got = O.rot6d_to_axis_angle(torch.tensor(gold["d6"])).numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - gold["aa"]).max() <= 1e-6
