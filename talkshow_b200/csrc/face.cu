@@ -4,6 +4,7 @@
 // ([B,T,C]) so that every Conv1d / Linear is one implicit GEMM (kernels.h); GroupNorm(512,512),
 // LayerNorm, the 50->30 fps interpolation and the 12-head attention are small dedicated kernels.
 // fp32 throughout (the parity bar is 1e-4 max-abs on the 103 outputs).
+#include <cuda_fp16.h>
 #include "convstack.h"
 #include "pixelcnn.h"
 
@@ -485,10 +486,183 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma_kernel(const 
   }
 }
 
+// ---- same algorithm on the fp16 MMA shape (m16n8k16, half the MMA count of the tf32 version) ---------
+// fp32 accuracy from a two-term fp16 split x = h + l (h = fp16(x), l = fp16(x - h): 22 significant bits),
+// products l*h + h*l + h*h accumulated in fp32.  P is scaled by 2^10 before the split so its low part stays
+// out of the fp16 subnormal range; q/k/v of a wav2vec2 layer are O(1..100), far inside the fp16 range.
+constexpr int ATT_LDK = 72;   // K row stride (floats): 64-bit fragment loads conflict-free per half-warp
+constexpr int ATT_LDV = 68;   // V row stride: 32-bit fragment loads conflict-free
+__device__ __forceinline__ void split_h2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                            float* __restrict__ out_lo, int T, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int Tp = (T + 63) & ~63;
+  float* Ks = sm;                                  // [Tp][ATT_LDK]
+  float* Vs = sm + (size_t)Tp * ATT_LDK;           // [Tp][ATT_LDV]
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ld = 3 * H * 64;
+  const float* base = qkv + (size_t)b * T * ld + h * 64;
+  for (int i = tid; i < Tp * 16; i += ATT_WARPS * 32) {
+    const int r = i >> 4, c4 = (i & 15) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (r < T) {
+      kv = *reinterpret_cast<const float4*>(base + (size_t)r * ld + H * 64 + c4);
+      vv = *reinterpret_cast<const float4*>(base + (size_t)r * ld + 2 * H * 64 + c4);
+    }
+    *reinterpret_cast<float4*>(Ks + r * ATT_LDK + c4) = kv;
+    *reinterpret_cast<float4*>(Vs + r * ATT_LDV + c4) = vv;
+  }
+  __syncthreads();
+  const int nrb = (T + 15) >> 4;
+  for (int rb = warp; rb < nrb; rb += ATT_WARPS) {
+    const int ra = rb * 16 + g, rbw = ra + 8;
+    // Q fragments per 16-wide d step: a0 = (row g, d 2t..2t+1), a1 = (row g+8, same), a2 = (row g, d 2t+8..9), a3 = (row g+8, same)
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
+      if (ra < T) {
+        x0 = *reinterpret_cast<const float2*>(base + (size_t)ra * ld + ks * 16 + 2 * t);
+        x2 = *reinterpret_cast<const float2*>(base + (size_t)ra * ld + ks * 16 + 2 * t + 8);
+      }
+      if (rbw < T) {
+        x1 = *reinterpret_cast<const float2*>(base + (size_t)rbw * ld + ks * 16 + 2 * t);
+        x3 = *reinterpret_cast<const float2*>(base + (size_t)rbw * ld + ks * 16 + 2 * t + 8);
+      }
+      split_h2(x0.x * scale, x0.y * scale, qh[ks][0], ql[ks][0]);
+      split_h2(x1.x * scale, x1.y * scale, qh[ks][1], ql[ks][1]);
+      split_h2(x2.x * scale, x2.y * scale, qh[ks][2], ql[ks][2]);
+      split_h2(x3.x * scale, x3.y * scale, qh[ks][3], ql[ks][3]);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+    for (int kb = 0; kb < Tp; kb += 64) {
+      float sc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      // S = Q K^T: B fragment (k = d, n = key): b0 = K[key = kb + 8 nt + g][16 ks + 2t .. +1], b1 = ...[16 ks + 2t + 8 .. +9]
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float* kr = Ks + (kb + nt * 8 + g) * ATT_LDK + ks * 16 + 2 * t;
+          const float2 k0 = *reinterpret_cast<const float2*>(kr), k1 = *reinterpret_cast<const float2*>(kr + 8);
+          uint32_t bh0, bl0, bh1, bl1;
+          split_h2(k0.x, k0.y, bh0, bl0);
+          split_h2(k1.x, k1.y, bh1, bl1);
+          mma_f16(sc[nt], ql[ks], bh0, bh1);
+          mma_f16(sc[nt], qh[ks], bl0, bl1);
+          mma_f16(sc[nt], qh[ks], bh0, bh1);
+        }
+      }
+      float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = kb + nt * 8 + 2 * t;
+        if (key >= T) sc[nt][0] = sc[nt][2] = -INFINITY;
+        if (key + 1 >= T) sc[nt][1] = sc[nt][3] = -INFINITY;
+        mx_a = fmaxf(mx_a, fmaxf(sc[nt][0], sc[nt][1]));
+        mx_b = fmaxf(mx_b, fmaxf(sc[nt][2], sc[nt][3]));
+      }
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+      const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+      const float ca = expf(m_a - mn_a), cb = expf(m_b - mn_b);
+      m_a = mn_a; m_b = mn_b;
+      l_a *= ca; l_b *= cb;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= ca; o[dt][1] *= ca; o[dt][2] *= cb; o[dt][3] *= cb; }
+      // O += P V per 16-key step j2: A = accumulator fragments of n-tiles 2 j2 (keys 2t, 2t+1) and 2 j2 + 1 (keys 2t+8, 2t+9);
+      // B fragment (k = key, n = d): b0 = V[kb + 16 j2 + 2t .. +1][8 dt + g], b1 = V[kb + 16 j2 + 2t + 8 .. +9][8 dt + g]
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        if (kb + j2 * 16 >= T) break;     // whole 16-key step is padding (warp-uniform)
+        float p[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          p[q * 4 + 0] = expf(sc[2 * j2 + q][0] - mn_a);
+          p[q * 4 + 1] = expf(sc[2 * j2 + q][1] - mn_a);
+          p[q * 4 + 2] = expf(sc[2 * j2 + q][2] - mn_b);
+          p[q * 4 + 3] = expf(sc[2 * j2 + q][3] - mn_b);
+        }
+        l_a += (p[0] + p[1]) + (p[4] + p[5]);
+        l_b += (p[2] + p[3]) + (p[6] + p[7]);
+        uint32_t ph[4], pl[4];
+        split_h2(p[0] * 1024.f, p[1] * 1024.f, ph[0], pl[0]);   // a0: row g,   keys 2t, 2t+1
+        split_h2(p[2] * 1024.f, p[3] * 1024.f, ph[1], pl[1]);   // a1: row g+8
+        split_h2(p[4] * 1024.f, p[5] * 1024.f, ph[2], pl[2]);   // a2: row g,   keys 2t+8, 2t+9
+        split_h2(p[6] * 1024.f, p[7] * 1024.f, ph[3], pl[3]);   // a3: row g+8
+        const float* vr = Vs + (kb + j2 * 16 + 2 * t) * ATT_LDV + g;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          uint32_t bh0, bl0, bh1, bl1;
+          split_h2(vr[dt * 8], vr[ATT_LDV + dt * 8], bh0, bl0);
+          split_h2(vr[8 * ATT_LDV + dt * 8], vr[9 * ATT_LDV + dt * 8], bh1, bl1);
+          mma_f16(o[dt], pl, bh0, bh1);
+          mma_f16(o[dt], ph, bl0, bl1);
+          mma_f16(o[dt], ph, bh0, bh1);
+        }
+      }
+    }
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+    const float ia = 1.0f / (l_a * 1024.f), ib = 1.0f / (l_b * 1024.f);
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = half ? rbw : ra;
+        if (row >= T) continue;
+        const float inv = half ? ib : ia;
+        const float v0 = o[dt][half * 2] * inv, v1 = o[dt][half * 2 + 1] * inv;
+        const size_t at = ((size_t)b * T + row) * (H * 64) + h * 64 + dt * 8 + 2 * t;
+        if (out_lo) {
+          const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+          *reinterpret_cast<float2*>(out + at) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(out_lo + at) = make_float2(v0 - h0, v1 - h1);
+        } else {
+          *reinterpret_cast<float2*>(out + at) = make_float2(v0, v1);
+        }
+      }
+    }
+  }
+}
+
 static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
+  static const int att_mode = getenv("TS_ATT_MMA") ? atoi(getenv("TS_ATT_MMA")) : 2;   // A/B switch: 0 FFMA, 1 tf32 MMA, 2 fp16-split MMA
+  if (att_mode == 2) {
+    const int Tp64 = (T + 63) & ~63;
+    const size_t smem16 = (size_t)Tp64 * (ATT_LDK + ATT_LDV) * sizeof(float);
+    if (smem16 <= 220 * 1024) {
+      TS_CUDA(cudaFuncSetAttribute(attention_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+      attention_mma16_kernel<<<B * H, ATT_WARPS * 32, smem16, s>>>(qkv, out, out_lo, T, H, 0.125f);
+      e->launches++;
+      TS_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   {
-    static const bool use_mma = !(getenv("TS_ATT_MMA") && atoi(getenv("TS_ATT_MMA")) == 0);   // A/B switch
+    const bool use_mma = att_mode != 0;
     const int Tp64 = (T + 63) & ~63;
     const size_t smem_mma = (size_t)2 * Tp64 * ATT_LD * sizeof(float);
     if (use_mma && smem_mma <= 220 * 1024) {

@@ -279,7 +279,7 @@ def test_rot6d_to_axis_angle(eng):
     assert torch.isfinite(got).all()
     ang = ref.norm(dim=-1)
     ok = ang < math.pi - 0.1
-    assert ok.sum() > 4000
+    assert ok.sum() > 3500
     assert (got[ok] - ref[ok]).abs().max().item() <= 1e-4
 
     def rotmat(a):      # Rodrigues in float64
