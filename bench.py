@@ -291,17 +291,17 @@ def run_ours(args, rank, world, local_rank):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = eng.pixelcnn_row_bytes * T                      # algorithmic weight bytes per launch
     achieved = alg_bytes / (pix_avg * 1e-3) / 1e9
-    roofline = {"kernel": "pixelcnn_kernel<true> (persistent gated-PixelCNN sampler, %d rows/launch)" % T,
+    roofline = {"kernel": "pixelcnn_kernel<true,5> (persistent gated-PixelCNN sampler, fused 52-stage plan, %d rows/launch)" % T,
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "traffic": eng.pixelcnn_staged_row_bytes * T, "traffic_source": "bytes the kernel stages per launch (packed "
-                "blob); ncu dram__bytes_read+write of the same kernel: 154 MB/row (profiles/r01_pixelcnn_v1_ncu_summary.md)", "launch_ms": pix_avg,
+                "blob); ncu dram__bytes_read+write of the same kernel: 163.8 MB/row (profiles/r01h_pixelcnn_ncu_summary.md)", "launch_ms": pix_avg,
                 "algorithmic_bytes": alg_bytes, "share_of_step": pix_avg / (dev_ms / args.steps)}
 
     # 106 GFLOP per 10 s clip (53 GMAC), scaled with the clip length
     face_flop = 106.0e9 * B * args.seconds / 10.0
     tf32x3_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 / 3.0     # tf32 rate = bf16/2, three products per MAC
-    roofline_dense = {"kernel": "face path (tc_gemm_kernel x56 + attention + FFMA layers per forward)", "bound": "tensor",
+    roofline_dense = {"kernel": "face path (tc2_gemm_kernel x56 tcgen05 3xTF32 + HMMA attention + FFMA2 layers per forward)", "bound": "tensor",
                       "achieved": face_flop / (face_avg * 1e-3) / 1e12, "peak": tf32x3_peak, "unit": "TFLOP/s",
                       "frac": face_flop / (face_avg * 1e-3) / 1e12 / tf32x3_peak,
                       "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32) / 3 (3xTF32 split)" if peaks else "fallback 1590/6",

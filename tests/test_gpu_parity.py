@@ -280,7 +280,15 @@ def test_rot6d_to_axis_angle(eng):
     ang = ref.norm(dim=-1)
     ok = ang < math.pi - 0.1
     assert ok.sum() > 3500
-    assert (got[ok] - ref[ok]).abs().max().item() <= 1e-4
+    # Tolerance 1e-3: the quaternion components are 0.5*sqrt(1 +- m00 +- m11 +- m22), so a small axis component is the
+    # square root of a cancellation residue — the reference's own fp32 result is 3.0e-4 away from a float64 evaluation
+    # of the same formula on these inputs (measured); two fp32 evaluations agree to that noise, not to 1e-4.
+    exact = O.rot6d_to_axis_angle(torch.tensor(gold["d6"]).double())
+    assert (ref[ok].double() - exact[ok]).abs().max().item() <= 1e-3
+    err = (got[ok] - ref[ok]).abs().max().item()
+    print("rot6d -> axis-angle max-abs vs reference golden (angle < pi - 0.1): %.3e" % err)
+    assert err <= 1e-3
+    assert (got[ok].double() - exact[ok]).abs().max().item() <= 1e-3
 
     def rotmat(a):      # Rodrigues in float64
         a = a.double()
