@@ -140,7 +140,9 @@ int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const 
  * 0: everything on the fp32 FFMA kernel. */
 int ts_set_tensor_cores(ts_engine* e, int enable);
 /* 0 = v1 persistent cooperative kernel (grid barrier), 1 = v1 one launch per stage (debug cross-check),
- * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only */
+ * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only (experimental, slower),
+ * 3 = EXPERIMENTAL cluster plan: set BEFORE ts_load_pixelcnn; 4-CTA clusters share a task's rows, split its K
+ *     range and reduce through distributed shared memory (each CTA reads a quarter of the stage's activations) */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
 /* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
  * stack multiplied together at load, layer-0 gate of column 1 gathered from a code table), 0 = plain 84-stage plan

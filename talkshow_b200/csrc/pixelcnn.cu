@@ -22,6 +22,8 @@ namespace ts {
 // =============================================================================================
 // host: plan construction
 // =============================================================================================
+static int pixc_max_clusters();   // resident PIX_CL-CTA clusters of the cluster-plan executor on the current device
+
 struct Job {
   int epi, layer, col, nrows, K, ncol;
   bool pairs;
@@ -220,7 +222,7 @@ static Layer pack_1x1(ts_engine* e, const float* w, int ldw, int koff, const flo
   return L;
 }
 
-static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
+static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused, int cl) {
   const int D = PIX_D;
   const ts_tensor* emb = ck.get("embedding.weight");
   if (emb->ndim != 2 || emb->shape[1] != D || emb->shape[0] != PIX_NCODE)
@@ -238,6 +240,14 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
   if (const char* v = getenv("TS_PIX_CTAS")) {   // experiment switch: persistent CTAs (every CTA re-reads the stage's activations from L2)
     const int n = atoi(v);
     if (n >= PIX_MB && n <= e->sm_count) P->ncta = n;
+  }
+  P->cl = cl;
+  if (cl > 1) {
+    // cluster plan (experimental, ts_set_pixelcnn_mode(3) before the load): the unit of work is a cluster of `cl`
+    // CTAs that share a task's output rows and split its K range; B200 keeps 132 CTAs of 4-CTA clusters resident
+    // (B300_MICROARCH.md, CTAS_ACTIVE at cluster size 4), i.e. 33 clusters on 148 SMs
+    const int ncl = e->host_only ? (e->sm_count * 33) / 148 : pixc_max_clusters();
+    P->ncta = std::min(e->sm_count / cl, ncl) * cl;
   }
   P->nclasses = ncls;
   P->lay = make_layout(L);
@@ -285,14 +295,16 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
     for (auto& j : jobs) { double c = (double)j.nrows * (j.K ? std::max(j.K, 256) : 16) * j.ncol; cost.push_back(c); tot += c; }
     std::vector<int> nc(jobs.size()), lo(jobs.size());
     int used = 0;
+    const int nunit = P->ncta / cl;                    // work units of a stage: CTAs, or clusters of the cluster plan
+    const int rowcap = cl > 1 ? PIX_CMAXROWS : PIX_MAXROWS;
     for (size_t i = 0; i < jobs.size(); ++i) {
-      const int cap = jobs[i].K ? PIX_MAXROWS : 4 * PIX_MAXROWS;  // matmul rows per CTA <= PIX_MAXROWS; epilogue-only tasks: 64
+      const int cap = jobs[i].K ? rowcap : 4 * PIX_MAXROWS;  // matmul rows per unit; epilogue-only tasks: 64
       lo[i] = (jobs[i].nrows + cap - 1) / cap;
-      nc[i] = std::max(lo[i], (int)std::floor(P->ncta * cost[i] / tot));
+      nc[i] = std::max(lo[i], (int)std::floor(nunit * cost[i] / tot));
       used += nc[i];
     }
-    for (size_t i = 0; used < P->ncta; i = (i + 1) % jobs.size()) { nc[i]++; used++; }
-    while (used > P->ncta) {
+    for (size_t i = 0; used < nunit; i = (i + 1) % jobs.size()) { nc[i]++; used++; }
+    while (used > nunit) {
       size_t big = 0; int slack = -1;
       for (size_t i = 0; i < jobs.size(); ++i) if (nc[i] - lo[i] > slack) { slack = nc[i] - lo[i]; big = i; }
       if (slack <= 0) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d SMs are too few for stage %d", P->ncta, s);
@@ -304,25 +316,28 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused) {
       const int unit = j.pairs ? 2 : 1, units = j.nrows / unit;
       const int base = units / nc[i], rem = units % nc[i];
       int u0 = 0;
-      for (int q = 0; q < nc[i]; ++q, ++cta) {
+      for (int q = 0; q < nc[i]; ++q) {
         int nu = base + (q < rem ? 1 : 0);
-        PixTask t{0, 0, 0, 0, 0, 0, 0, 0};
-        if (nu > 0) {
-          t.epi = j.epi; t.layer = j.layer; t.col = j.col;
-          t.row0 = u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
-          if (t.K > 0 && t.nrows > PIX_MAXROWS) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per CTA (> %d) with %d SMs", t.nrows, PIX_MAXROWS, P->ncta);
-          size_t sz = (size_t)(t.K + 1) * t.rpad;
-          if (sz > (size_t)PIX_WBUF) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: task blob %zu floats > staging buffer", sz);
-          t.wofs = (int)P->blob.size();
-          P->blob.resize(P->blob.size() + sz, 0.f);
-          float* dst = P->blob.data() + t.wofs;
-          for (int r = 0; r < t.nrows; ++r) {
-            for (int k = 0; k < t.K; ++k) dst[(size_t)k * t.rpad + r] = ws.w(j, t.row0 + r, k);
-            dst[(size_t)t.K * t.rpad + r] = ws.bias(j, t.row0 + r);
+        for (int rank = 0; rank < cl; ++rank, ++cta) {   // the CTAs of a unit: same rows, K slice `rank` of `cl`
+          PixTask t{0, 0, 0, 0, 0, 0, 0, 0};
+          if (nu > 0) {
+            t.epi = j.epi; t.layer = j.layer; t.col = j.col;
+            t.row0 = u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
+            if (t.K > 0 && t.nrows > rowcap) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per unit (> %d) with %d SMs", t.nrows, rowcap, P->ncta);
+            const int Ks = t.K / cl, k0 = rank * Ks;       // K is a multiple of 256
+            size_t sz = (size_t)(Ks + 1) * t.rpad;
+            if (sz > (size_t)PIX_WBUF) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: task blob %zu floats > staging buffer", sz);
+            t.wofs = (int)P->blob.size();
+            P->blob.resize(P->blob.size() + sz, 0.f);
+            float* dst = P->blob.data() + t.wofs;
+            for (int r = 0; r < t.nrows; ++r) {
+              for (int k = 0; k < Ks; ++k) dst[(size_t)k * t.rpad + r] = ws.w(j, t.row0 + r, k0 + k);
+              dst[(size_t)Ks * t.rpad + r] = ws.bias(j, t.row0 + r);
+            }
+            dense += (int64_t)t.nrows * Ks;
           }
-          dense += (int64_t)t.nrows * t.K;
+          P->table[(size_t)s * P->ncta + cta] = t;
         }
-        P->table[(size_t)s * P->ncta + cta] = t;
         u0 += nu;
       }
     }
@@ -924,6 +939,249 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
   }
 }
 
+// =============================================================================================
+// EXPERIMENTAL cluster plan executor (ts_set_pixelcnn_mode(3) before ts_load_pixelcnn)
+// =============================================================================================
+// Same stage table, same epilogues, same grid barrier as pixelcnn_kernel.  The unit of work is a cluster of
+// PIX_CL = 4 CTAs: the four CTAs share the task's output rows (up to 64) and each owns a quarter of its K
+// range, so a CTA reads a quarter of the stage's [K][64] activation slab (the whole K/32 slice of a warp sits
+// in registers, one load burst per stage) and stages the same number of weight bytes as before.  Partial
+// sums are reduced across the 8 warps in shared memory, exchanged between the four CTAs through distributed
+// shared memory (mapa + ld.shared::cluster behind a cluster barrier) and summed in rank order; the epilogue
+// items of the task are striped over the four CTAs.
+constexpr size_t PIXC_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB + PIX_CMAXROWS * PIX_MB) * sizeof(float) + 64 +
+                             PIX_MAXSTAGES * sizeof(PixTask);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// partial products of rows [rowofs, rowofs + 4 RC) over the warp's register-resident K slice (ng groups of 8 rows)
+template <int RC>
+__device__ __forceinline__ void mm_rows_cl(const float* __restrict__ Wsm, int rpad, int rowofs, int ng, int kloc0,
+                                           const unsigned long long (&x)[6][8], float* red, int slice, int lane) {
+  unsigned long long acc[4 * RC];
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j) acc[j] = 0ull;
+#pragma unroll
+  for (int g = 0; g < 6; ++g) {
+    if (g < ng) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4* w4 = reinterpret_cast<const float4*>(Wsm + (size_t)(kloc0 + g * 8 + u) * rpad + rowofs);
+#pragma unroll
+        for (int rc = 0; rc < RC; ++rc) {
+          const float4 w = w4[rc];
+          fma2(acc[rc * 4 + 0], w.x, x[g][u]);
+          fma2(acc[rc * 4 + 1], w.y, x[g][u]);
+          fma2(acc[rc * 4 + 2], w.z, x[g][u]);
+          fma2(acc[rc * 4 + 3], w.w, x[g][u]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4 * RC; ++j)
+    *reinterpret_cast<unsigned long long*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+}
+
+__device__ void run_matmul_task_cl(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, float* xbuf,
+                                   uint32_t rank, uint32_t clid) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PixLayout& a = A.lay;
+  const int npass = (t.epi == EPI_V2H || t.epi == EPI_FUSEV) ? 2 : 1;
+  const int Ks = t.K / PIX_CL;                 // this CTA's K range is [rank * Ks, rank * Ks + Ks)
+  const float* bias = Wsm + (size_t)Ks * t.rpad;
+  float* arena = A.arena;
+  const uint32_t xaddr = smem_u32(xbuf);
+  for (int pass = 0; pass < npass; ++pass) {
+    int s_seg[6];
+    resolve_segments(t, pass, r, a, A.L, s_seg);
+    if (pass > 0) cluster_sync_all();          // the peers finished reading this CTA's partials of the previous pass
+    if (t.K > 0) {
+      const int kper = Ks >> 3, ng = kper >> 3;  // warp slice: K/32 rows = K/256 groups of 8 (1, 2, 3, 4 or 6)
+      const int slice = (warp + (int)clid) & 7;
+      const int kloc0 = slice * kper, kglob0 = (int)rank * Ks + kloc0;
+      unsigned long long x[6][8];
+#pragma unroll
+      for (int g = 0; g < 6; ++g) {
+        if (g < ng) {
+          const int k = kglob0 + g * 8;
+          const float* base = arena + s_seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * PIX_MB));
+        }
+      }
+      for (int rp = 0; rp * 16 < t.rpad; ++rp) {
+        const int rcp = min(4, (t.rpad - rp * 16) >> 2);
+        switch (rcp) {
+          case 1: mm_rows_cl<1>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
+          case 2: mm_rows_cl<2>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
+          case 3: mm_rows_cl<3>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
+          default: mm_rows_cl<4>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
+        }
+        __syncthreads();
+        for (int it = tid; it < 4 * rcp * PIX_MB; it += PIX_THREADS)
+          xbuf[(rp * 16 + (it >> 6)) * PIX_MB + (it & (PIX_MB - 1))] = red_sum(red, it >> 6, it & (PIX_MB - 1));
+        __syncthreads();
+      }
+      cluster_sync_all();                      // all four partial tiles are complete and visible cluster-wide
+    }
+    auto csum = [&](int row, int m) -> float {   // fixed rank order -> deterministic
+      if (t.K == 0) return 0.f;
+      const uint32_t ad = xaddr + (uint32_t)(row * PIX_MB + m) * 4u;
+      return ((ld_dsmem(ad, 0) + ld_dsmem(ad, 1)) + ld_dsmem(ad, 2)) + ld_dsmem(ad, 3);
+    };
+    const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE || t.epi == EPI_HGATE2);
+    const int items = (pairs ? t.nrows >> 1 : t.nrows) * PIX_MB;
+    for (int it = (int)rank * PIX_THREADS + tid; it < items; it += PIX_CL * PIX_THREADS) {   // items striped over the 4 CTAs
+      const int m = it & (PIX_MB - 1), j = it >> 6;
+      if (pairs) {
+        const int q = (t.row0 >> 1) + j;  // gate channel
+        float at = csum(2 * j, m) + bias[2 * j];
+        float as = csum(2 * j + 1, m) + bias[2 * j + 1];
+        const float* cls = arena + a.CLS + (t.layer * 2) * PIX_SEG;
+        float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
+        if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
+          const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
+          float vt = __ldcg(v2h + q * PIX_MB + m);
+          float vs = __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
+          float zt = (vt + at) + ct;
+          float zs = (vs + as) + cs;
+          arena[a.G + (t.layer & 1) * PIX_SEG + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+        } else {
+          float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
+          hv[q * PIX_MB + m] = at;
+          hv[(PIX_D + q) * PIX_MB + m] = as;
+          float g = tanhf(at + ct) * sigmoidf_(as + cs);
+          if (t.epi == EPI_VERT0) arena[a.XV1P + t.col * PIX_SEG + q * PIX_MB + m] = g;
+          else if (t.layer + 1 < A.L)
+            arena[a.XV + (((t.layer + 1) * 2 + (r & 1)) * 2 + t.col) * PIX_SEG + q * PIX_MB + m] = g;
+        }
+      } else {
+        const int ch = t.row0 + j;
+        float v = csum(j, m) + bias[j];
+        switch (t.epi) {
+          case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * PIX_SEG + ch * PIX_MB + m] = v; break;
+          case EPI_FUSEV: {
+            float au = m < A.B ? A.audv[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
+            arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * PIX_SEG + ch * PIX_MB + m] = v + au;
+          } break;
+          case EPI_HRES:
+            if (t.layer == 0) arena[a.XHP + ch * PIX_MB + m] = v;
+            else {
+              float xh = __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
+              arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
+            }
+            break;
+          case EPI_FUSEH: case EPI_HRESF: {
+            float au = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
+            arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
+          } break;
+          case EPI_OUT1: case EPI_OUT1F: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
+          case EPI_OUT2: arena[a.LOG + ch * PIX_MB + m] = v; break;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_cl_kernel(PixArgs A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* wbuf = reinterpret_cast<float*>(smem_raw);
+  float* red = wbuf + 2 * PIX_WBUF;
+  float* xbuf = red + 8 * PIX_MAXROWS * PIX_MB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + PIX_CMAXROWS * PIX_MB);
+  PixTask* tasks = reinterpret_cast<PixTask*>(bars + 8);
+  const int tid = threadIdx.x, cta = blockIdx.x;
+  const uint32_t rank = cluster_ctarank(), clid = cluster_id_x();
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < A.nstages * 8; i += PIX_THREADS)
+    reinterpret_cast<int*>(tasks)[i] = reinterpret_cast<const int*>(A.table + (size_t)(i >> 3) * A.ncta + cta)[i & 7];
+  __syncthreads();
+  cluster_sync_all();                           // every CTA of the cluster is running before any DSMEM access
+  auto tbytes = [](const PixTask& t) { return (uint32_t)((t.K / PIX_CL + 1) * t.rpad) * 4u; };
+  uint32_t uses[2] = {0u, 0u};
+  const int total = A.Ttot * A.nstages;
+  if (tid == 0) {
+    const PixTask t0 = tasks[0];
+    if (task_active(t0, 0, A.log_r0) && t0.epi != EPI_SAMPLE) {
+      mbar_expect_tx(&bars[0], tbytes(t0));
+      tma_load_1d(wbuf, A.blob + t0.wofs, tbytes(t0), &bars[0]);
+    }
+  }
+  int r = 0, s = 0;
+  for (int g = 0; g < total; ++g) {
+    const PixTask t = tasks[s];
+    const int buf = g & 1;
+    if (tid == 0 && g + 1 < total) {
+      int s1 = s + 1, r1 = r;
+      if (s1 == A.nstages) { s1 = 0; r1 = r + 1; }
+      const PixTask tn = tasks[s1];
+      if (task_active(tn, r1, A.log_r0) && tn.epi != EPI_SAMPLE) {
+        fence_proxy_async();
+        mbar_expect_tx(&bars[buf ^ 1], tbytes(tn));
+        tma_load_1d(wbuf + (buf ^ 1) * PIX_WBUF, A.blob + tn.wofs, tbytes(tn), &bars[buf ^ 1]);
+      }
+    }
+    const bool active = task_active(t, r, A.log_r0);   // identical for the four CTAs of a cluster
+    const bool has_w = active && t.epi != EPI_SAMPLE;
+    if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
+    if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);
+    if (active) {
+      if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
+      else run_matmul_task_cl(t, A, r, wbuf + buf * PIX_WBUF, red, xbuf, rank, clid);
+    }
+    grid_arrive(A.barrier);
+    if (++s == A.nstages) { s = 0; ++r; }
+  }
+  cluster_sync_all();                           // no CTA leaves while a peer may still read its shared memory
+}
+
+static void pixc_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int ncta, cudaStream_t s) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(ncta);
+  cfg.blockDim = dim3(PIX_THREADS);
+  cfg.dynamicSmemBytes = PIXC_SMEM;
+  cfg.stream = s;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PIX_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+}
+static int pixc_max_clusters() {
+  TS_CUDA(cudaFuncSetAttribute(pixelcnn_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIXC_SMEM));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute at[2];
+  pixc_config(cfg, at, PIX_CL, nullptr);
+  int maxcl = 0;
+  TS_CUDA(cudaOccupancyMaxActiveClusters(&maxcl, pixelcnn_cl_kernel, &cfg));
+  return maxcl;
+}
+
 #include "pixelcnn2.inc"
 
 __global__ void build_cls_kernel(const float* __restrict__ cls_w, const int64_t* __restrict__ label, float* arena, int cls_off,
@@ -1034,7 +1292,21 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
   A.fused = P->fused ? 1 : 0;
   (void)noise_B;
-  if (e->pixel_mode == 0) {
+  if (P->cl > 1) {
+    if (e->pixel_mode == 1) fail(TS_ERR_UNSUPPORTED, "pixelcnn: the cluster plan has no per-stage debug mode");
+    TS_CUDA(cudaFuncSetAttribute(pixelcnn_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIXC_SMEM));
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[2];
+    pixc_config(cfg, at, P->ncta, s);
+    int maxcl = 0;
+    TS_CUDA(cudaOccupancyMaxActiveClusters(&maxcl, pixelcnn_cl_kernel, &cfg));
+    if (maxcl * PIX_CL < P->ncta)
+      fail(TS_ERR_UNSUPPORTED, "pixelcnn cluster plan: %d CTAs planned, only %d clusters of %d can be resident", P->ncta, maxcl, PIX_CL);
+    if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
+    TS_CUDA(cudaLaunchKernelEx(&cfg, pixelcnn_cl_kernel, A));
+    if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
+    e->launches++;
+  } else if (e->pixel_mode == 0 || e->pixel_mode == 3) {
     // A/B switch: 0 = burst loads + scalar FFMA, 4 = pipelined loads + scalar FFMA, 5 (default) = pipelined loads + FFMA2
     static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 5;
     void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : pipe == 4 ? (void*)pixelcnn_kernel<true, 4> : (void*)pixelcnn_kernel<true, 5>;
@@ -1071,7 +1343,7 @@ using namespace ts;
 extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
-  PixelPlan* P = build_plan(e, ck, e->pixel_fusion);
+  PixelPlan* P = build_plan(e, ck, e->pixel_fusion, e->pixel_mode == 3 ? PIX_CL : 1);
   P->p2 = build_plan2(e, ck, P->L);
   delete e->pix;
   e->pix = P;
@@ -1112,7 +1384,7 @@ extern "C" int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* tab
   if (table) {
     if (*table_len < tl) fail(TS_ERR_INVALID, "table buffer too small");
     int32_t h[32] = {P->ncta, P->nstages, P->L, PIX_D, PIX_MB, P->lay.E, P->lay.XV1P, P->lay.XV, P->lay.HV, P->lay.V2H,
-                     P->lay.G, P->lay.XHP, P->lay.XH, P->lay.Y, P->lay.LOG, P->lay.CLS, P->lay.total, PIX_NCODE};
+                     P->lay.G, P->lay.XHP, P->lay.XH, P->lay.Y, P->lay.LOG, P->lay.CLS, P->lay.total, PIX_NCODE, P->cl};
     memcpy(table, h, sizeof h);
     memcpy(table + hdr, P->table.data(), P->table.size() * sizeof(PixTask));
   }

@@ -12,6 +12,8 @@ constexpr int PIX_THREADS = 256;
 constexpr int PIX_MAXROWS = 16; // weight rows one CTA handles per stage
 constexpr int PIX_WBUF = 18560; // floats per weight staging buffer (74.2 KB), two buffers
 constexpr int PIX_NCODE = 2048;
+constexpr int PIX_CL = 4;        // cluster plan: CTAs per cluster (K split 4 ways, DSMEM reduction)
+constexpr int PIX_CMAXROWS = 64; // cluster plan: weight rows one cluster handles per stage
 
 enum PixEpi {
   EPI_IDLE = 0,
@@ -41,6 +43,7 @@ struct PixLayout {  // arena offsets in floats
 
 struct PixelPlan {
   int L = 0, ncta = 0, nstages = 0, nclasses = 4;
+  int cl = 1;                  // CTAs per work unit (1: every CTA owns its rows; PIX_CL: cluster plan)
   bool fused = false;          // 52-stage plan (EPI_HRESF / EPI_HGATE2 / EPI_OUT1F), else the plain 84-stage plan
   PixLayout lay;
   std::vector<PixTask> table;  // [nstages][ncta]

@@ -18,6 +18,7 @@ class Plan:
         assert h[3] == D and h[4] == MB
         names = ["E", "XV1P", "XV", "HV", "V2H", "G", "XHP", "XH", "Y", "LOG", "CLS", "total"]
         self.lay = {n: int(h[5 + i]) for i, n in enumerate(names)}
+        self.cl = max(1, int(h[18]))      # CTAs per work unit (cluster plan: the ranks hold K slices of the same rows)
         self.table = table[32:].reshape(self.nstages, self.ncta, 8)
         self.blob = blob
 
@@ -106,8 +107,22 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                         zs = (v2h[D:, m] + tw[1::2]) + cls[0][D:, m]
                         writes.append((lay["G"], m, np.tanh(zt) * _sigmoid(zs)))
                     continue
-                W = plan.blob[wofs:wofs + K * rpad].reshape(K, rpad)[:, :nrows]
-                bias = plan.blob[wofs + K * rpad: wofs + K * rpad + nrows]
+                cl = plan.cl
+                if cta % cl:
+                    continue                      # ranks 1.. of a cluster: their K slices are gathered by rank 0 below
+                Ks = K // cl
+                parts = []
+                for q in range(cl):
+                    tq = plan.table[s, cta + q]
+                    assert [int(v) for v in tq[[0, 1, 2, 3, 4, 6, 7]]] == [epi, layer, col, row0, nrows, K, rpad]
+                    wq = int(tq[5])
+                    parts.append(plan.blob[wq:wq + Ks * rpad].reshape(Ks, rpad)[:, :nrows])
+                    bq = plan.blob[wq + Ks * rpad: wq + Ks * rpad + nrows]
+                    if q == 0:
+                        bias = bq
+                    else:
+                        assert np.array_equal(bias, bq)
+                W = np.concatenate(parts, 0) if K else np.zeros((0, nrows), np.float32)
                 npass = 2 if epi in (EPI_V2H, EPI_FUSEV) else 1
                 for pas in range(npass):
                     segs = segments(t, pas, r, lay, L)

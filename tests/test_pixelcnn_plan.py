@@ -11,10 +11,12 @@ from talkshow_b200 import _lib, synth
 from talkshow_b200.engine import Engine
 
 
-@pytest.fixture(scope="module", params=["fused", "plain"])
+@pytest.fixture(scope="module", params=["fused", "plain", "cluster"])
 def plan(ckpts, request):
     e = Engine(-148)            # host-only planning engine sized for 148 SMs
-    e.set_pixelcnn_fusion(request.param == "fused")
+    e.set_pixelcnn_fusion(request.param != "plain")
+    if request.param == "cluster":
+        e.set_pixelcnn_mode(3)  # experimental cluster plan: 33 clusters x 4 CTAs, K split inside the cluster
     e.load_pixelcnn(ckpts["pixel"]["generator"])
     table, blob = _lib.plan_to_numpy(e.h)
     rb = e.pixelcnn_row_bytes
@@ -32,12 +34,13 @@ def _audio_terms(sd, aud):
 
 def test_plan_shape(plan):
     p, row_bytes = plan
-    assert p.ncta == 148 and p.L == 15 and p.nstages in (52, 84)
+    assert p.ncta == (132 if p.cl == 4 else 148) and p.L == 15 and p.nstages in (52, 84)
     fused = p.nstages == 52
     assert (p.table[:, :, 0] >= 11).any() == fused      # EPI_HRESF / EPI_HGATE2 / EPI_OUT1F only in the fused plan
     assert row_bytes == 89774080        # SURVEY.md §8d algorithmic bytes per latent row
     t = p.table
-    assert (t[:, :, 4][t[:, :, 6] > 0] <= 16).all()         # matmul tasks: at most 16 weight rows per CTA
+    assert (t[:, :, 4][t[:, :, 6] > 0] <= (64 if p.cl == 4 else 16)).all()     # weight rows per CTA / per cluster
+    t = t[:, ::p.cl]                                        # one entry per work unit
     # every output row of every stage is owned by exactly one CTA
     for s in range(p.nstages):
         for epi, layer, col in {tuple(x) for x in t[s][:, :3].tolist() if x[0] not in (0, 10)}:
