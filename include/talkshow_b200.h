@@ -134,7 +134,7 @@ int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, flo
  * mode 0 = fp32 FFMA kernel, mode 1 = tcgen05 3xTF32 tensor-core kernel (K % 32 == 0). */
 int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N,
                   int K, int act, void* stream);
-/* Dense-contraction kernel selection (all parity-tested):
+/* Dense-contraction kernel selection (default covered by the GPU tests; the others by scratch/ab_tc.py):
  * 1 (default) / 3: tcgen05 3xTF32 kernel, CTA pair (cta_group::2) 256x256 tile;
  * 4: tcgen05 3xTF32 kernel, single CTA 128x256 tile; 2: same in clusters with TMA multicast of the operand boxes;
  * 0: everything on the fp32 FFMA kernel. */
