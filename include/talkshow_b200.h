@@ -144,6 +144,15 @@ int ts_set_tensor_cores(ts_engine* e, int enable);
  * 3 = EXPERIMENTAL cluster plan: set BEFORE ts_load_pixelcnn; 4-CTA clusters share a task's rows, split its K
  *     range and reduce through distributed shared memory (each CTA reads a quarter of the stage's activations) */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
+/* Debug: per-stage, per-CTA globaltimer stamps of one latent row of the persistent kernel.  ts_pixelcnn_trace(e, row)
+ * arms it (row < 0 disarms) for the following ts_pixelcnn_generate calls; ts_pixelcnn_trace_read copies
+ * out[stages][ctas][4] = {weights ready, left the grid barrier, task done, arrived} in ns (*len in/out, elements;
+ * out may be NULL to query the size). */
+/* stages per latent row and persistent CTAs of the loaded plan */
+int ts_pixelcnn_plan_shape(ts_engine* e, int* nstages, int* ncta);
+int ts_pixelcnn_trace(ts_engine* e, int row);
+int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len);
+
 /* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
  * stack multiplied together at load, layer-0 gate of column 1 gathered from a code table), 0 = plain 84-stage plan
  * (one stage per reference conv).  Both evaluate GatedPixelCNN.forward exactly up to fp32 rounding order. */

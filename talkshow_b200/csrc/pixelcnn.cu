@@ -401,6 +401,8 @@ struct PixArgs {
   unsigned* barrier;
   PixLayout lay;
   int B, T0, Ttot, log_r0, L, nstages, ncta, fused;
+  unsigned long long* trace;   // [nstages][ncta][4] globaltimer stamps of row trace_row (debug builds of the kernel only)
+  int trace_row;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -867,7 +869,16 @@ __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m
 constexpr int PIX_MAXSTAGES = 160;  // this CTA's column of the stage table is kept in shared memory
 constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB) * sizeof(float) + 64 + PIX_MAXSTAGES * sizeof(PixTask);
 
-template <bool PERSISTENT, int PIPE>
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// TRACE: a second instantiation of the persistent kernel that stamps, for one latent row, when each CTA's thread 0
+// has its weights, leaves the grid barrier, finishes its task and has arrived again (ts_pixelcnn_trace): the
+// measurement the stage cost model and the CTA split should be fitted to.  The default kernel is TRACE = false.
+template <bool PERSISTENT, int PIPE, bool TRACE = false>
 __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int r_single, int s_single) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* wbuf = reinterpret_cast<float*>(smem_raw);
@@ -929,12 +940,19 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     pre.a = pre.b = 0.f; pre.valid = false;
     if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue(t, A, r);   // in flight while we wait below
     if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
+    unsigned long long* tr = nullptr;
+    if constexpr (TRACE) {
+      if (tid == 0 && r == A.trace_row && A.trace) { tr = A.trace + ((size_t)s * A.ncta + cta) * 4; tr[0] = globaltimer_ns(); }
+    }
     if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);  // every CTA finished stage g-1
+    if constexpr (TRACE) { if (tr) tr[1] = globaltimer_ns(); }
     if (active) {
       if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
       else run_matmul_task<PIPE>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
+    if constexpr (TRACE) { __syncthreads(); if (tr) tr[2] = globaltimer_ns(); }
     grid_arrive(A.barrier);
+    if constexpr (TRACE) { if (tr) tr[3] = globaltimer_ns(); }
     if (++s == A.nstages) { s = 0; ++r; }
   }
 }
@@ -1291,6 +1309,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   A.barrier = P->d_barrier; A.lay = P->lay;
   A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
   A.fused = P->fused ? 1 : 0;
+  A.trace = P->d_trace; A.trace_row = P->trace_row;
   (void)noise_B;
   if (P->cl > 1) {
     if (e->pixel_mode == 1) fail(TS_ERR_UNSUPPORTED, "pixelcnn: the cluster plan has no per-stage debug mode");
@@ -1310,6 +1329,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     // A/B switch: 0 = burst loads + scalar FFMA, 4 = pipelined loads + scalar FFMA, 5 (default) = pipelined loads + FFMA2
     static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 5;
     void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : pipe == 4 ? (void*)pixelcnn_kernel<true, 4> : (void*)pixelcnn_kernel<true, 5>;
+    if (P->d_trace && P->trace_row >= 0) fn = (void*)pixelcnn_kernel<true, 5, true>;
     TS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
@@ -1373,6 +1393,42 @@ extern "C" double ts_pixelcnn_last_ms(ts_engine* e) {
   if (cudaEventSynchronize(e->pix->ev1) != cudaSuccess) return -1.0;
   if (cudaEventElapsedTime(&ms, e->pix->ev0, e->pix->ev1) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+
+// Stage trace of one latent row (debug): row >= 0 arms it for the following ts_pixelcnn_generate calls (the
+// TRACE instantiation of the persistent kernel runs instead of the default one), row < 0 disarms.
+extern "C" int ts_pixelcnn_trace(ts_engine* e, int row) {
+  TS_API_BEGIN(e)
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  if (e->host_only) fail(TS_ERR_UNSUPPORTED, "host-only engine cannot execute");
+  PixelPlan* P = e->pix;
+  const size_t n = (size_t)P->nstages * P->ncta * 4;
+  if (row >= 0 && !P->d_trace) P->d_trace = (unsigned long long*)e->dmalloc(n * sizeof(unsigned long long));
+  if (row >= 0) TS_CUDA(cudaMemset(P->d_trace, 0, n * sizeof(unsigned long long)));
+  P->trace_row = row;
+  TS_API_END(e)
+}
+// out[nstages][ncta][4] (ns): weights ready / left the grid barrier / task done / arrived.  *len in/out (elements).
+extern "C" int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len) {
+  TS_API_BEGIN(e)
+  if (!e->pix || !e->pix->d_trace) fail(TS_ERR_NOT_LOADED, "pixelcnn trace not armed");
+  PixelPlan* P = e->pix;
+  const int64_t n = (int64_t)P->nstages * P->ncta * 4;
+  if (out) {
+    if (*len < n) fail(TS_ERR_INVALID, "trace buffer too small");
+    TS_CUDA(cudaDeviceSynchronize());
+    TS_CUDA(cudaMemcpy(out, P->d_trace, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
+  *len = n;
+  TS_API_END(e)
+}
+
+extern "C" int ts_pixelcnn_plan_shape(ts_engine* e, int* nstages, int* ncta) {
+  TS_API_BEGIN(e)
+  if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  *nstages = e->pix->nstages;
+  *ncta = e->pix->ncta;
+  TS_API_END(e)
 }
 
 extern "C" int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len) {

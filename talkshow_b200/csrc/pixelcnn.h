@@ -59,6 +59,8 @@ struct PixelPlan {
   unsigned* d_barrier = nullptr;
   Layer emb_aud, fuse_v_a, fuse_h_a;  // audio terms (precomputed per call for all rows)
   void* p2 = nullptr;          // Plan2 of the cluster-per-8-samples kernel (pixelcnn2.inc)
+  unsigned long long* d_trace = nullptr;  // stage trace buffer (ts_pixelcnn_trace)
+  int trace_row = -1;
   bool timing = false, pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int64_t timed_rows = 0, timed_launches = 0;

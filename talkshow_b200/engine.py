@@ -75,6 +75,21 @@ class Engine:
     def set_tensor_cores(self, enable=True):
         self._check(self.L.ts_set_tensor_cores(self.h, int(enable)), "ts_set_tensor_cores")
 
+    def pixelcnn_trace(self, row):
+        """Arm (row >= 0) / disarm (row < 0) the per-stage, per-CTA time stamps of one latent row (debug)."""
+        self._check(self.L.ts_pixelcnn_trace(self.h, int(row)), "ts_pixelcnn_trace")
+
+    def pixelcnn_trace_read(self):
+        """-> int64 tensor [stages, ctas, 4] (ns): weights ready, left the grid barrier, task done, arrived."""
+        import ctypes as C
+        n = C.c_int64(0)
+        self._check(self.L.ts_pixelcnn_trace_read(self.h, None, C.byref(n)), "ts_pixelcnn_trace_read")
+        buf = torch.zeros(n.value, dtype=torch.int64)
+        self._check(self.L.ts_pixelcnn_trace_read(self.h, buf.data_ptr(), C.byref(n)), "ts_pixelcnn_trace_read")
+        ns, nc = C.c_int(0), C.c_int(0)
+        self._check(self.L.ts_pixelcnn_plan_shape(self.h, C.byref(ns), C.byref(nc)), "ts_pixelcnn_plan_shape")
+        return buf.view(ns.value, nc.value, 4)
+
     def set_pixelcnn_fusion(self, on):
         """Plan built by the next load_pixelcnn: fused 52-stage (default) or plain 84-stage."""
         self._check(self.L.ts_set_pixelcnn_fusion(self.h, int(bool(on))), "ts_set_pixelcnn_fusion")
