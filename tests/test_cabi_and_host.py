@@ -54,6 +54,13 @@ def test_host_only_engine_rejects_execution_and_bad_checkpoints():
     e.load_pixelcnn(sd)
     assert e.pixelcnn_row_bytes == 89774080
     assert e.pixelcnn_staged_row_bytes > e.pixelcnn_row_bytes
+    import ctypes as C
+    ns, nc = C.c_int(0), C.c_int(0)
+    assert e.L.ts_pixelcnn_plan_shape(e.h, C.byref(ns), C.byref(nc)) == 0 and (ns.value, nc.value) == (52, 148)
+    with pytest.raises(RuntimeError, match="host-only"):
+        e.pixelcnn_trace(0)
+    with pytest.raises(ValueError):
+        e.rot6d_to_axis_angle(torch.zeros(4, 5))
     e.close()
 
 
