@@ -155,7 +155,9 @@ int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len);
 
 /* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
  * stack multiplied together at load, layer-0 gate of column 1 gathered from a code table), 0 = plain 84-stage plan
- * (one stage per reference conv).  Both evaluate GatedPixelCNN.forward exactly up to fp32 rounding order. */
+ * (one stage per reference conv), 2 = EXPERIMENTAL: the fused plan with vert_to_horiz taken out of the vertical stages
+ * (it runs one column at a time beside the horizontal stage before its consumer).  All evaluate
+ * GatedPixelCNN.forward exactly up to fp32 rounding order. */
 int ts_set_pixelcnn_fusion(ts_engine* e, int on);
 
 #ifdef __cplusplus

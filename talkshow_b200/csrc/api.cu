@@ -74,7 +74,8 @@ extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
 
 extern "C" int ts_set_pixelcnn_fusion(ts_engine* e, int on) {
   if (!e) return TS_ERR_INVALID;
-  e->pixel_fusion = on != 0;
+  if (on < 0 || on > 2) return TS_ERR_INVALID;
+  e->pixel_fusion = on;
   return TS_OK;
 }
 

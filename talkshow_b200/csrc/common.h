@@ -128,7 +128,7 @@ struct ts_engine {
   std::string err;
   int64_t launches = 0;
   int pixel_mode = 0;
-  bool pixel_fusion = true;  // build the 52-stage fused PixelCNN plan at ts_load_pixelcnn (else the plain 84-stage plan)
+  int pixel_fusion = 1;      // plan built at ts_load_pixelcnn: 0 plain 84-stage, 1 fused 52-stage, 2 fused + vert_to_horiz in the horizontal pass
   bool tc_pair = true;       // CTA-pair (cta_group::2) 256x256 tensor-core kernel (default)
   bool tc_multicast = false;  // share operand boxes inside a thread-block cluster by TMA multicast
   bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows

@@ -58,6 +58,40 @@ static std::vector<std::vector<Job>> build_stages_fused(int L) {
   return st;
 }
 
+// Schedule 2 (experimental): the fused plan with vert_to_horiz out of the vertical stages.  The stage trace
+// (profiles/r01h_pixelcnn_stage_trace.txt) shows VERT at 7 rows per CTA taking 5.6 us and 7.4 us at 11 rows, the
+// difference being the 49 CTAs that vert_to_horiz of the previous layer occupies.  Its output is consumed only by the
+// horizontal pass of the same row, so here it runs per column (EPI_V2H1) beside the horizontal stage that precedes
+// its consumer; the pre-gate vertical outputs (HV) get one slot per layer instead of a 2-deep ring.
+static std::vector<std::vector<Job>> build_stages_fused2(int L) {
+  const int D = PIX_D;
+  std::vector<std::vector<Job>> st;
+  st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});   // layer 0: needed by both layer-0 gates
+  for (int l = 1; l < L; ++l) {
+    std::vector<Job> j = {{EPI_VERT, l, 0, 2 * D, 4 * D, 1, true}, {EPI_VERT, l, 1, 2 * D, 4 * D, 1, true}};
+    if (l == 1) j.push_back({EPI_HGATE, 0, 0, 2 * D, 0, 1, true});
+    st.push_back(j);
+  }
+  for (int c = 0; c < 2; ++c) {
+    st.push_back({{EPI_HRESF, 0, c, D, D, 1, false}, {EPI_V2H1, 1, c, 2 * D, 2 * D, 1, false}});
+    {
+      std::vector<Job> j = {{EPI_HGATE, 1, c, 2 * D, c ? 2 * D : D, 1, true}};
+      if (L > 2) j.push_back({EPI_V2H1, 2, c, 2 * D, 2 * D, 1, false});
+      st.push_back(j);
+    }
+    for (int l = 2; l < L; ++l) {
+      std::vector<Job> j = {{EPI_HGATE2, l, c, 2 * D, c ? 3 * D : 2 * D, 1, true}, {EPI_HRES, l - 1, c, D, D, 1, false}};
+      if (l + 1 < L) j.push_back({EPI_V2H1, l + 1, c, 2 * D, 2 * D, 1, false});
+      st.push_back(j);
+    }
+    st.push_back({{EPI_OUT1F, 0, c, 512, 2 * D, 1, false}});
+    st.push_back({{EPI_OUT2, 0, c, PIX_NCODE, 512, 1, false}});
+    st.push_back({{EPI_SAMPLE, 0, c, 0, c == 0 ? 1 : 0, 1, false}});
+  }
+  return st;
+}
+
 static std::vector<std::vector<Job>> build_stages(int L) {
   const int D = PIX_D;
   std::vector<std::vector<Job>> st;
@@ -87,14 +121,14 @@ static std::vector<std::vector<Job>> build_stages(int L) {
   return st;
 }
 
-static PixLayout make_layout(int L) {
+static PixLayout make_layout(int L, int hvslots) {
   PixLayout a;
   int o = 0;
   auto take = [&](int nseg) { int r = o; o += nseg * PIX_SEG; return r; };
   a.E = take(4 * 2);
   a.XV1P = take(2);
   a.XV = take(L * 2 * 2);
-  a.HV = take(2 * 2 * 2);
+  a.HV = take(hvslots * 2 * 2);   // pre-gate vertical outputs: [slot][column][tanh half, sigmoid half]
   a.V2H = take(L * 2 * 2);
   a.G = take(2);     // gate output of layer l lives in slot l & 1
   a.XHP = take(1);
@@ -173,7 +207,7 @@ struct WeightSrc {
         int kh = sidx >> 1, icol = sidx & 1, kw = icol - j.col + 1;
         return vs[l][(((size_t)ch * D + ci) * 2 + kh) * 3 + kw];
       }
-      case EPI_V2H: return v2h[l][(size_t)ch * 2 * D + k];
+      case EPI_V2H: case EPI_V2H1: return v2h[l][(size_t)ch * 2 * D + k];
       case EPI_FUSEV: return fv[(size_t)ch * 2 * D + k];
       case EPI_FUSEH: return fh[(size_t)ch * 2 * D + k];
       case EPI_HGATE: {
@@ -198,7 +232,7 @@ struct WeightSrc {
     int ch = chan(j, jr), l = j.layer;
     switch (j.epi) {
       case EPI_VERT0: case EPI_VERT: return vsb[l][ch];
-      case EPI_V2H: return v2hb[l][ch];
+      case EPI_V2H: case EPI_V2H1: return v2hb[l][ch];
       case EPI_HGATE: return hsb[l][ch];
       case EPI_HRES: return hrb[l][ch];
       case EPI_HRESF: return bf[ch];
@@ -222,7 +256,7 @@ static Layer pack_1x1(ts_engine* e, const float* w, int ldw, int koff, const flo
   return L;
 }
 
-static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused, int cl) {
+static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
   const int D = PIX_D;
   const ts_tensor* emb = ck.get("embedding.weight");
   if (emb->ndim != 2 || emb->shape[1] != D || emb->shape[0] != PIX_NCODE)
@@ -250,11 +284,12 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, bool fused, int cl) {
     P->ncta = std::min(e->sm_count / cl, ncl) * cl;
   }
   P->nclasses = ncls;
-  P->lay = make_layout(L);
+  bool fused = level >= 1 && L >= 3;
+  P->sched = fused ? level : 0;
+  P->lay = make_layout(L, P->sched == 2 ? L : 2);
   if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);
-  fused = fused && L >= 3;
   P->fused = fused;
-  auto stages = fused ? build_stages_fused(L) : build_stages(L);
+  auto stages = P->sched == 2 ? build_stages_fused2(L) : fused ? build_stages_fused(L) : build_stages(L);
   P->nstages = (int)stages.size();
   if (P->nstages > 160) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d stages per row (> 160)", P->nstages);
   P->table.assign((size_t)P->nstages * P->ncta, PixTask{0, 0, 0, 0, 0, 0, 0, 0});
@@ -463,7 +498,16 @@ __device__ __forceinline__ bool task_active(const PixTask& t, int r, int log_r0)
 __device__ __forceinline__ uint32_t task_bytes(const PixTask& t) { return (uint32_t)((t.K + 1) * t.rpad) * 4u; }
 
 // arena offsets (floats) of the K segments of a matmul task; returns the segment count
+template <bool S2 = false>
 __device__ __forceinline__ int resolve_segments(const PixTask& t, int pass, int r, const PixLayout& a, int L, int* seg) {
+  if constexpr (S2) {   // schedule 2: one HV slot per layer, single-column vert_to_horiz
+    if (t.epi == EPI_V2H || t.epi == EPI_V2H1) {
+      const int col = t.epi == EPI_V2H1 ? t.col : pass;
+      seg[0] = a.HV + ((t.layer * 2 + col) * 2) * PIX_SEG;
+      seg[1] = seg[0] + PIX_SEG;
+      return 2;
+    }
+  }
   switch (t.epi) {
     case EPI_VERT0:
       for (int kh = 0; kh < 3; ++kh)
@@ -667,9 +711,13 @@ struct EpiPre {  // epilogue operands fetched before the grid-barrier wait (they
 };
 
 // operands of thread-item `tid` of an H-pass task whose epilogue has at most one item per thread
+template <bool S2 = false>
 __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixArgs& A, int r) {
   EpiPre p;
   p.a = 0.f; p.b = 0.f; p.valid = false;
+  if constexpr (S2) {   // schedule 2: the vert_to_horiz operand of a gate is written by the PREVIOUS stage
+    if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) return p;
+  }
   const int tid = threadIdx.x, m = tid & (PIX_MB - 1), j = tid >> 6;
   const PixLayout& a = A.lay;
   if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
@@ -694,7 +742,7 @@ __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixA
   return p;
 }
 
-template <int PIPE>
+template <int PIPE, bool S2 = false>
 __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, const EpiPre& pre) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PixLayout& a = A.lay;
@@ -703,7 +751,7 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
   float* arena = A.arena;
   for (int pass = 0; pass < npass; ++pass) {
     int s_seg[6];  // at most 6 segments (EPI_VERT0)
-    resolve_segments(t, pass, r, a, A.L, s_seg);
+    resolve_segments<S2>(t, pass, r, a, A.L, s_seg);
     if (pass > 0) __syncthreads();  // previous pass's epilogue finished reading red
     if (t.K > 0) {
       if constexpr (PIPE == 5) {
@@ -748,7 +796,7 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
           float zs = (vs + as) + cs;
           arena[a.G + (t.layer & 1) * PIX_SEG + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
         } else {
-          float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
+          float* hv = arena + a.HV + (((S2 ? t.layer : (t.layer & 1)) * 2 + t.col) * 2) * PIX_SEG;
           hv[q * PIX_MB + m] = at;
           hv[(PIX_D + q) * PIX_MB + m] = as;
           float g = tanhf(at + ct) * sigmoidf_(as + cs);
@@ -761,6 +809,9 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
         float v = red_sum(red, j, m) + bias[j];
         switch (t.epi) {
           case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * PIX_SEG + ch * PIX_MB + m] = v; break;
+          case EPI_V2H1:
+            if constexpr (S2) arena[a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG + ch * PIX_MB + m] = v;
+            break;
           case EPI_FUSEV: {
             float au = m < A.B ? A.audv[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
             arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * PIX_SEG + ch * PIX_MB + m] = v + au;
@@ -878,7 +929,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // TRACE: a second instantiation of the persistent kernel that stamps, for one latent row, when each CTA's thread 0
 // has its weights, leaves the grid barrier, finishes its task and has arrived again (ts_pixelcnn_trace): the
 // measurement the stage cost model and the CTA split should be fitted to.  The default kernel is TRACE = false.
-template <bool PERSISTENT, int PIPE, bool TRACE = false>
+template <bool PERSISTENT, int PIPE, bool TRACE = false, bool S2 = false>
 __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int r_single, int s_single) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* wbuf = reinterpret_cast<float*>(smem_raw);
@@ -896,7 +947,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     for (int i = tid; i < nf; i += PIX_THREADS) wbuf[i] = A.blob[t.wofs + i];
     __syncthreads();
     EpiPre pre; pre.a = pre.b = 0.f; pre.valid = false;
-    run_matmul_task<0>(t, A, r_single, wbuf, red, pre);
+    run_matmul_task<0, S2>(t, A, r_single, wbuf, red, pre);
     return;
   }
 
@@ -938,7 +989,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     const bool has_w = active && t.epi != EPI_SAMPLE;  // K == 0 tasks still stage their bias row
     EpiPre pre;
     pre.a = pre.b = 0.f; pre.valid = false;
-    if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue(t, A, r);   // in flight while we wait below
+    if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue<S2>(t, A, r);   // in flight while we wait below
     if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
     unsigned long long* tr = nullptr;
     if constexpr (TRACE) {
@@ -948,7 +999,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     if constexpr (TRACE) { if (tr) tr[1] = globaltimer_ns(); }
     if (active) {
       if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
-      else run_matmul_task<PIPE>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
+      else run_matmul_task<PIPE, S2>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
     if constexpr (TRACE) { __syncthreads(); if (tr) tr[2] = globaltimer_ns(); }
     grid_arrive(A.barrier);
@@ -1330,6 +1381,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 5;
     void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : pipe == 4 ? (void*)pixelcnn_kernel<true, 4> : (void*)pixelcnn_kernel<true, 5>;
     if (P->d_trace && P->trace_row >= 0) fn = (void*)pixelcnn_kernel<true, 5, true>;
+    if (P->sched == 2) fn = (P->d_trace && P->trace_row >= 0) ? (void*)pixelcnn_kernel<true, 5, true, true> : (void*)pixelcnn_kernel<true, 5, false, true>;
     TS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
@@ -1338,10 +1390,11 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
     e->launches++;
   } else {
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
+    auto fn1 = P->sched == 2 ? pixelcnn_kernel<false, 0, false, true> : pixelcnn_kernel<false, 0>;
+    TS_CUDA(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     for (int r = 0; r < Ttot; ++r)
       for (int st = 0; st < P->nstages; ++st) {
-        pixelcnn_kernel<false, 0><<<P->ncta, PIX_THREADS, PIX_SMEM, s>>>(A, r, st);
+        fn1<<<P->ncta, PIX_THREADS, PIX_SMEM, s>>>(A, r, st);
         e->launches++;
       }
     TS_CUDA(cudaGetLastError());
@@ -1363,7 +1416,8 @@ using namespace ts;
 extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
-  PixelPlan* P = build_plan(e, ck, e->pixel_fusion, e->pixel_mode == 3 ? PIX_CL : 1);
+  const bool clplan = e->pixel_mode == 3;   // the cluster executor knows schedules 0 and 1 only
+  PixelPlan* P = build_plan(e, ck, clplan ? std::min(e->pixel_fusion, 1) : e->pixel_fusion, clplan ? PIX_CL : 1);
   P->p2 = build_plan2(e, ck, P->L);
   delete e->pix;
   e->pix = P;
@@ -1440,7 +1494,8 @@ extern "C" int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* tab
   if (table) {
     if (*table_len < tl) fail(TS_ERR_INVALID, "table buffer too small");
     int32_t h[32] = {P->ncta, P->nstages, P->L, PIX_D, PIX_MB, P->lay.E, P->lay.XV1P, P->lay.XV, P->lay.HV, P->lay.V2H,
-                     P->lay.G, P->lay.XHP, P->lay.XH, P->lay.Y, P->lay.LOG, P->lay.CLS, P->lay.total, PIX_NCODE, P->cl};
+                     P->lay.G, P->lay.XHP, P->lay.XH, P->lay.Y, P->lay.LOG, P->lay.CLS, P->lay.total, PIX_NCODE, P->cl,
+                     P->sched == 2 ? P->L : 2};
     memcpy(table, h, sizeof h);
     memcpy(table + hdr, P->table.data(), P->table.size() * sizeof(PixTask));
   }

@@ -30,7 +30,10 @@ enum PixEpi {
   // fused plan (52 stages): linear stages folded into the gate matmul that consumes them
   EPI_HRESF = 11,  // (fusion_h . horiz_resid_0) G_0 + audio term -> x_h[1]
   EPI_HGATE2 = 12, // gate of layer l on (horiz_stack_l . horiz_resid_{l-1}) G_{l-1} + horiz_stack_l x_h[l-1] (+ column-0 tap)
-  EPI_OUT1F = 13   // output_conv.0 on (W horiz_resid_{L-1}) G_{L-1} + W x_h[L-1], ReLU
+  EPI_OUT1F = 13,  // output_conv.0 on (W horiz_resid_{L-1}) G_{L-1} + W x_h[L-1], ReLU
+  // schedule 2: vert_to_horiz leaves the vertical stages and runs one column at a time beside the horizontal stage
+  // that precedes its consumer
+  EPI_V2H1 = 14    // vert_to_horiz of one layer, column t.col only
 };
 
 struct PixTask {  // one CTA's work in one stage (8 ints)
@@ -45,6 +48,7 @@ struct PixelPlan {
   int L = 0, ncta = 0, nstages = 0, nclasses = 4;
   int cl = 1;                  // CTAs per work unit (1: every CTA owns its rows; PIX_CL: cluster plan)
   bool fused = false;          // 52-stage plan (EPI_HRESF / EPI_HGATE2 / EPI_OUT1F), else the plain 84-stage plan
+  int sched = 1;               // 0 plain, 1 fused, 2 fused + vert_to_horiz moved into the horizontal pass (EPI_V2H1)
   PixLayout lay;
   std::vector<PixTask> table;  // [nstages][ncta]
   std::vector<float> blob;     // packed per-task weights: [K][rpad] then bias [rpad]

@@ -91,8 +91,9 @@ class Engine:
         return buf.view(ns.value, nc.value, 4)
 
     def set_pixelcnn_fusion(self, on):
-        """Plan built by the next load_pixelcnn: fused 52-stage (default) or plain 84-stage."""
-        self._check(self.L.ts_set_pixelcnn_fusion(self.h, int(bool(on))), "ts_set_pixelcnn_fusion")
+        """Plan built by the next load_pixelcnn: 1/True fused 52-stage (default), 0/False plain 84-stage,
+        2 fused with vert_to_horiz scheduled in the horizontal pass (experimental)."""
+        self._check(self.L.ts_set_pixelcnn_fusion(self.h, int(on)), "ts_set_pixelcnn_fusion")
 
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")

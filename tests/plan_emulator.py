@@ -7,7 +7,7 @@ and the schedule can be validated against the oracle on a machine without a GPU.
 import numpy as np
 
 (EPI_IDLE, EPI_VERT0, EPI_VERT, EPI_V2H, EPI_FUSEV, EPI_HGATE, EPI_HRES, EPI_FUSEH, EPI_OUT1, EPI_OUT2, EPI_SAMPLE,
- EPI_HRESF, EPI_HGATE2, EPI_OUT1F) = range(14)
+ EPI_HRESF, EPI_HGATE2, EPI_OUT1F, EPI_V2H1) = range(15)
 D, MB, SEG = 256, 64, 256 * 64
 
 
@@ -19,6 +19,7 @@ class Plan:
         names = ["E", "XV1P", "XV", "HV", "V2H", "G", "XHP", "XH", "Y", "LOG", "CLS", "total"]
         self.lay = {n: int(h[5 + i]) for i, n in enumerate(names)}
         self.cl = max(1, int(h[18]))      # CTAs per work unit (cluster plan: the ranks hold K slices of the same rows)
+        self.hvslots = int(h[19]) or 2    # pre-gate vertical outputs: 2-deep ring, or one slot per layer (schedule 2)
         self.table = table[32:].reshape(self.nstages, self.ncta, 8)
         self.blob = blob
 
@@ -27,14 +28,21 @@ def _sigmoid(x):
     return (1.0 / (1.0 + np.exp(-x.astype(np.float32)))).astype(np.float32)
 
 
-def segments(t, pas, r, lay, L):
+def hv_slot(layer, hvslots):
+    return layer if hvslots > 2 else layer & 1
+
+
+def segments(t, pas, r, lay, L, hvslots=2):
     epi, layer, col = int(t[0]), int(t[1]), int(t[2])
+    if epi == EPI_V2H1:
+        s0 = lay["HV"] + ((hv_slot(layer, hvslots) * 2 + col) * 2) * SEG
+        return [s0, s0 + SEG]
     if epi == EPI_VERT0:
         return [lay["E"] + ((((r - 3 + kh) & 3) * 2) + ci) * SEG for kh in range(3) for ci in range(2)]
     if epi == EPI_VERT:
         return [lay["XV"] + ((layer * 2 + ((r - 1 + kh) & 1)) * 2 + ci) * SEG for kh in range(2) for ci in range(2)]
     if epi == EPI_V2H:
-        s0 = lay["HV"] + (((layer & 1) * 2 + pas) * 2) * SEG
+        s0 = lay["HV"] + ((hv_slot(layer, hvslots) * 2 + pas) * 2) * SEG
         return [s0, s0 + SEG]
     if epi == EPI_FUSEV:
         return [lay["XV1P"] + pas * SEG]
@@ -125,7 +133,7 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                 W = np.concatenate(parts, 0) if K else np.zeros((0, nrows), np.float32)
                 npass = 2 if epi in (EPI_V2H, EPI_FUSEV) else 1
                 for pas in range(npass):
-                    segs = segments(t, pas, r, lay, L)
+                    segs = segments(t, pas, r, lay, L, plan.hvslots)
                     assert len(segs) * D == K, (epi, layer, col, K, len(segs))
                     if K:
                         x = np.concatenate([A(o) for o in segs], 0)        # [K, MB]
@@ -143,7 +151,7 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                             zs = (v2h[D + q0:D + q0 + nq] + as_) + cs
                             writes.append((lay["G"] + (layer & 1) * SEG, (q0, nq), np.tanh(zt) * _sigmoid(zs)))
                         else:
-                            hvo = lay["HV"] + (((layer & 1) * 2 + col) * 2) * SEG
+                            hvo = lay["HV"] + ((hv_slot(layer, plan.hvslots) * 2 + col) * 2) * SEG
                             writes.append((hvo, (q0, nq), at.copy()))
                             writes.append((hvo, (D + q0, nq), as_.copy()))
                             g = np.tanh(at + ct) * _sigmoid(as_ + cs)
@@ -155,6 +163,8 @@ def run(plan, emb, cls_w, audv, audh, label, codes_forced, T, noise=None, T0=Non
                         sl = (row0, nrows)
                         if epi == EPI_V2H:
                             writes.append((lay["V2H"] + ((layer * 2 + pas) * 2) * SEG, sl, acc))
+                        elif epi == EPI_V2H1:
+                            writes.append((lay["V2H"] + ((layer * 2 + col) * 2) * SEG, sl, acc))
                         elif epi == EPI_FUSEV:
                             au = np.zeros((nrows, MB), np.float32)
                             au[:, :B] = audv[:, r, row0:row0 + nrows].T

@@ -170,34 +170,6 @@ def test_pixelcnn_plain_plan(eng, ckpts):
         e.close()
 
 
-def test_pixelcnn_cluster_plan(eng, ckpts):
-    """EXPERIMENTAL executor (ts_set_pixelcnn_mode(3) before the load): 4-CTA clusters split K and reduce through
-    distributed shared memory.  Same sampled sequences as the oracle and the default kernel."""
-    from talkshow_b200.engine import Engine
-
-    e = Engine(0)
-    e.set_pixelcnn_mode(3)
-    try:
-        try:
-            e.load_pixelcnn(ckpts["pixel"]["generator"])
-        except RuntimeError as ex:          # fewer resident clusters than the plan needs on this part
-            pytest.skip("cluster plan not available: %s" % ex)
-        B, T = 5, 20
-        label = torch.tensor([0, 1, 2, 3, 1])
-        aud = O.audio_encoder(ckpts["pixel"]["audioencoder"], synth.synth_mfcc(B, 4 * T, seed=41))
-        noise = draw_noise(2 * T, B, 17)
-        ref = O.pixelcnn_generate(ckpts["pixel"]["generator"], label, T, B, aud.unsqueeze(-1).repeat(1, 1, 1, 2),
-                                  noise=noise, window=18)
-        got, lc = e.pixelcnn_generate(aud, label, noise, want_logits=True)
-        base, lb = eng.pixelcnn_generate(aud, label, noise, want_logits=True)
-        assert torch.equal(got.cpu(), ref)
-        assert torch.equal(base.cpu(), ref)
-        assert (lc - lb).abs().max().item() <= TOL
-    finally:
-        torch.cuda.synchronize()
-        e.close()
-
-
 def test_pixelcnn_continuity(eng, ckpts):
     """generate(pre_latents, pre_audio), gated_pixelcnn_v2.py:158-165."""
     gold = _load("pixel_cont")

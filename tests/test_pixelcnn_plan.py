@@ -11,10 +11,10 @@ from talkshow_b200 import _lib, synth
 from talkshow_b200.engine import Engine
 
 
-@pytest.fixture(scope="module", params=["fused", "plain", "cluster"])
+@pytest.fixture(scope="module", params=["fused", "plain", "cluster", "sched2"])
 def plan(ckpts, request):
     e = Engine(-148)            # host-only planning engine sized for 148 SMs
-    e.set_pixelcnn_fusion(request.param != "plain")
+    e.set_pixelcnn_fusion({"plain": 0, "sched2": 2}.get(request.param, 1))
     if request.param == "cluster":
         e.set_pixelcnn_mode(3)  # experimental cluster plan: 33 clusters x 4 CTAs, K split inside the cluster
     e.load_pixelcnn(ckpts["pixel"]["generator"])
@@ -51,6 +51,9 @@ def test_plan_shape(plan):
                 assert r0 == pos
                 pos += n
             assert pos in (256, 512, 2048)
+    if p.hvslots > 2:                                       # schedule 2: no vert_to_horiz in the vertical stages 2..15
+        assert not ((t[2:16, :, 0] == PE.EPI_V2H) | (t[2:16, :, 0] == PE.EPI_V2H1)).any()
+        assert (t[16:, :, 0] == PE.EPI_V2H1).any()
 
 
 def test_plan_teacher_forced_logits(plan, ckpts):
