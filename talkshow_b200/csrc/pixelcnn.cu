@@ -837,7 +837,10 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
 
 // softmax over 2048 logits + categorical draw = argmax(p / q) (ATen multinomial, num_samples = 1),
 // then embedding gather of the sampled code into the E ring.  One CTA per sample.
-__device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m, float* red) {
+// QPRE (schedule 2 only): the sampler noise of this position was loaded before the grid-barrier wait (it is an
+// input of the call, independent of every stage) and arrives in qpre[8].
+template <bool QPRE = false>
+__device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m, float* red, const float* qpre = nullptr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = t.col;
   float* sf = red;                                  // [8] scratch
@@ -883,7 +886,7 @@ __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int n = tid + 256 * j;
-      float v = (ex[j] / sum) / q[n];
+      float v = (ex[j] / sum) / (QPRE ? qpre[j] : q[n]);
       if (v > bv || (v == bv && n < bi)) { bv = v; bi = n; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -990,6 +993,14 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     EpiPre pre;
     pre.a = pre.b = 0.f; pre.valid = false;
     if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue<S2>(t, A, r);   // in flight while we wait below
+    float qpre[8];
+    if constexpr (S2) {
+      if (active && t.epi == EPI_SAMPLE && cta < A.B && r >= A.T0) {
+        const float* q = A.noise + ((size_t)(2 * (r - A.T0) + t.col) * A.B + cta) * PIX_NCODE;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qpre[j] = __ldcs(q + tid + 256 * j);
+      }
+    }
     if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
     unsigned long long* tr = nullptr;
     if constexpr (TRACE) {
@@ -998,7 +1009,10 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);  // every CTA finished stage g-1
     if constexpr (TRACE) { if (tr) tr[1] = globaltimer_ns(); }
     if (active) {
-      if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
+      if (t.epi == EPI_SAMPLE) {
+        if constexpr (S2) { if (cta < A.B) run_sample_task<true>(t, A, r, cta, red, qpre); }
+        else { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
+      }
       else run_matmul_task<PIPE, S2>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
     if constexpr (TRACE) { __syncthreads(); if (tr) tr[2] = globaltimer_ns(); }
