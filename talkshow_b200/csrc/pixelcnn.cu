@@ -327,7 +327,10 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
     // CTAs per job proportional to FMA cost
     std::vector<double> cost;
     double tot = 0;
-    for (auto& j : jobs) { double c = (double)j.nrows * (j.K ? std::max(j.K, 256) : 16) * j.ncol; cost.push_back(c); tot += c; }
+    // cost of a job ~ rows x (K + alpha): alpha (TS_PIX_ROWCOST, default 0 = FMA count) is the per-row fixed cost in units of
+    // K — the stage trace shows K = 256 tasks with 12-13 rows finishing last, i.e. rows cost more than their FMAs
+    static const double alpha = getenv("TS_PIX_ROWCOST") ? atof(getenv("TS_PIX_ROWCOST")) : 0.0;
+    for (auto& j : jobs) { double c = (double)j.nrows * (j.K ? std::max(j.K, 256) + alpha : 16) * j.ncol; cost.push_back(c); tot += c; }
     std::vector<int> nc(jobs.size()), lo(jobs.size());
     int used = 0;
     const int nunit = P->ncta / cl;                    // work units of a stage: CTAs, or clusters of the cluster plan
