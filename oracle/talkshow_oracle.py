@@ -231,6 +231,23 @@ def body_generate(ckpt, vq_ckpt, mfcc, label, noise=None, window=None):
     return lat, torch.cat([body, hand], 1).transpose(1, 2)
 
 
+def body_infer_continuity(ckpt, vq_ckpt, mfcc0, mfcc1, label, noise0=None, noise1=None, window=None):
+    """s2g_body_pixel.infer_on_audio(continuity=True), nets/smplx_body_pixel.py:244-269 + infer :291-304, after
+    get_mfcc_sepa (data_utils/utils.py:234-263): the 2 s prefix and the remainder are encoded SEPARATELY by the
+    audio encoder, the remainder is sampled with pre_latents / pre_audio of the prefix, and each chunk is decoded
+    SEPARATELY (Decoder.forward ignores pre_state, vqvae_1d.py:139-149) before the time-axis concat.
+    mfcc0 [B,64,M0], mfcc1 [B,64,M1] -> (lat0, lat1, poses [B,F0+F1,129])."""
+    B = mfcc0.shape[0]
+    a0 = audio_encoder(ckpt["audioencoder"], mfcc0).unsqueeze(-1).repeat(1, 1, 1, 2)
+    a1 = audio_encoder(ckpt["audioencoder"], mfcc1).unsqueeze(-1).repeat(1, 1, 1, 2)
+    lat0 = pixelcnn_generate(ckpt["generator"], label, a0.shape[2], B, a0, noise=noise0, window=window)
+    lat1 = pixelcnn_generate(ckpt["generator"], label, a1.shape[2], B, a1, noise=noise1, pre_latents=lat0, pre_audio=a0,
+                             window=window)
+    body = torch.cat([vq_decode(vq_ckpt["g_body"], lat0[..., 0]), vq_decode(vq_ckpt["g_body"], lat1[..., 0])], 2)
+    hand = torch.cat([vq_decode(vq_ckpt["g_hand"], lat0[..., 1]), vq_decode(vq_ckpt["g_hand"], lat1[..., 1])], 2)
+    return lat0, lat1, torch.cat([body, hand], 1).transpose(1, 2)
+
+
 _FIX_3D = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 21, 22, 23, 24, 25, 26,
            30, 31, 32, 33, 34, 35, 45, 46, 47, 48, 49, 50]
 C_INDEX_3D = [i for i in range(165) if i not in _FIX_3D]          # data_utils/lower_body.py:44-56
@@ -244,6 +261,19 @@ def body_vq_roundtrip(vq_ckpt, initial_pose):
     ih, rh = vq_roundtrip(vq_ckpt["g_hand"], gt[..., 39:])
     pred = torch.cat([rb, rh], 1).transpose(1, 2)                  # [B,F,129]
     return ib, ih, torch.cat(list(pred), 1)                        # np.concatenate(output, axis=1), :293
+
+
+def body_vq_continuity(vq_ckpt, initial_pose, chunk=60, nchunks=5):
+    """s2g_body_vq.infer_on_audio(continuity=True) :256-271: five 60-frame chunks, each round-tripped on its own
+    (pre_state is ignored by Decoder.forward), concatenated in time -> numpy-layout [5*60, B*129]."""
+    gt = initial_pose[:, C_INDEX_3D].permute(0, 2, 1)
+    bs, hs = [], []
+    for i in range(nchunks):
+        seg = gt[:, i * chunk:(i + 1) * chunk]
+        bs.append(vq_roundtrip(vq_ckpt["g_body"], seg[..., :39])[1])
+        hs.append(vq_roundtrip(vq_ckpt["g_hand"], seg[..., 39:])[1])
+    pred = torch.cat([torch.cat(bs, 2), torch.cat(hs, 2)], 1).transpose(1, 2)
+    return torch.cat(list(pred), 1)
 
 
 # ---------------------------------------------------------------------------------------------

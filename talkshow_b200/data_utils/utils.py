@@ -41,6 +41,21 @@ def mfcc_from_wave(audio, sr_0, sr=22000, fps=30):
     return mfcc(audio).squeeze(dim=0).transpose(0, 1).numpy()
 
 
+def get_mfcc_sepa(audio_fn, fps=15, sr=16000):
+    """Reference data_utils/utils.py:234-263 (same signature): features of the first 2 s and of the remainder computed
+    separately -> (numpy (M0+M1, 64), M0)."""
+    import torchaudio.transforms as ta_T
+
+    audio, sr_0 = load_wav(audio_fn)
+    if sr != sr_0:
+        audio = ta_T.Resample(sr_0, sr)(audio)
+    if audio.shape[0] > 1:
+        audio = torch.mean(audio, dim=0, keepdim=True)
+    f0 = mfcc_from_wave(audio[:, :sr * 2], sr, sr=sr, fps=fps)
+    f1 = mfcc_from_wave(audio[:, sr * 2:], sr, sr=sr, fps=fps)
+    return np.concatenate((f0, f1), axis=0), f0.shape[0]
+
+
 def get_mfcc_ta(audio_fn, eps=1e-6, fps=15, smlpx=False, sr=16000, n_mfcc=64, win_size=None, type="mfcc", am=None,
                 am_sr=None, encoder_choice="mfcc"):
     """Same signature as the reference.  ``am`` given + encoder_choice='faceformer' -> raw 16 kHz wave

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import torch
 
-from ..data_utils.utils import get_mfcc_ta, load_wav, mfcc_from_wave
+from ..data_utils.utils import get_mfcc_sepa, get_mfcc_ta, load_wav
 from .base import draw_sampler_noise, resolve_device, shared_engine, strip_module
 
 
@@ -100,26 +100,19 @@ class TrainWrapper:
         return poses
 
     def _infer_continuity(self, aud_fn, id, fps, sr, B):
-        """continuity=True (:260-269): a 2 s prefix, then the rest conditioned on the prefix's latents
-        and audio (GatedPixelCNN.generate(pre_latents, pre_audio))."""
-        audio, sr_0 = load_wav(aud_fn)
-        import torchaudio.transforms as ta_T
-        if sr != sr_0:
-            audio = ta_T.Resample(sr_0, sr)(audio)
-            sr_0 = sr
-        if audio.shape[0] > 1:
-            audio = torch.mean(audio, dim=0, keepdim=True)
-        cut = 2 * sr
-        f0 = mfcc_from_wave(audio[:, :cut], sr_0, sr=sr, fps=fps)        # get_mfcc_sepa, utils.py:234-263
-        f1 = mfcc_from_wave(audio[:, cut:], sr_0, sr=sr, fps=fps)
-        label = (torch.tensor([0]) if id is None else id.reshape(-1)).repeat(B)[:B]
-        m0 = torch.from_numpy(np.ascontiguousarray(f0.T))[None].repeat(B, 1, 1)
-        m1 = torch.from_numpy(np.ascontiguousarray(f1.T))[None].repeat(B, 1, 1)
+        """continuity=True (:244-269, infer :291-304): a 2 s prefix, then the rest conditioned on the prefix's latents
+        and audio (GatedPixelCNN.generate(pre_latents, pre_audio)).  The two chunks go through the audio encoder
+        separately and are DECODED separately — the reference's Decoder.forward ignores pre_state
+        (nets/spg/vqvae_1d.py:139-149), so each chunk sees zero padding at the 2 s seam."""
+        aud_feat, gap = get_mfcc_sepa(aud_fn, sr=sr, fps=fps)                 # (M0+M1, 64), M0
+        feat = torch.from_numpy(np.ascontiguousarray(np.asarray(aud_feat, dtype=np.float32).T))[None].repeat(B, 1, 1)
+        m0, m1 = feat[:, :, :gap].contiguous(), feat[:, :, gap:].contiguous()
+        label = torch.tensor([0]) if id is None else id.reshape(-1).repeat(B)
         a0, a1 = self.engine.audio_encode(m0), self.engine.audio_encode(m1)
         T0, T1 = a0.shape[2], a1.shape[2]
         lat0 = self.engine.pixelcnn_generate(a0, label, self._noise(T0, B))
         lat1 = self.engine.pixelcnn_generate(torch.cat([a0, a1], 2), label, self._noise(T1, B), T=T1, pre_latents=lat0)
-        lat = torch.cat([lat0, lat1], 1)
-        body = self.engine.vq_decode(0, lat[..., 0].contiguous())
-        hand = self.engine.vq_decode(1, lat[..., 1].contiguous())
+        self.last_codes = torch.cat([lat0, lat1], 1)
+        body = torch.cat([self.engine.vq_decode(0, lat[..., 0].contiguous()) for lat in (lat0, lat1)], 2)
+        hand = torch.cat([self.engine.vq_decode(1, lat[..., 1].contiguous()) for lat in (lat0, lat1)], 2)
         return torch.cat([body, hand], 1).transpose(1, 2).cpu().numpy()

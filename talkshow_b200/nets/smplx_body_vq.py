@@ -42,10 +42,18 @@ class TrainWrapper:
         argument is unused by the reference's VQ path too)."""
         assert self.args.infer, "train mode"
         if continuity:
-            raise NotImplementedError("continuity chunks of the VQ wrapper are outside the built path")
-        ib, ih = self.encode(initial_pose)
-        body = self.engine.vq_decode(0, ib)
-        hand = self.engine.vq_decode(1, ih)
+            # :256-271: five 60-frame chunks, each encoded/quantised/decoded on its own (pre_state is ignored by
+            # Decoder.forward, vqvae_1d.py:139-149) and concatenated along time
+            bs, hs = [], []
+            for i in range(5):
+                ib, ih = self.encode(initial_pose[:, :, i * 60:(i + 1) * 60])
+                bs.append(self.engine.vq_decode(0, ib))
+                hs.append(self.engine.vq_decode(1, ih))
+            body, hand = torch.cat(bs, 2), torch.cat(hs, 2)
+        else:
+            ib, ih = self.encode(initial_pose)
+            body = self.engine.vq_decode(0, ib)
+            hand = self.engine.vq_decode(1, ih)
         output = torch.cat([body, hand], 1).transpose(1, 2).cpu().numpy()          # (B,F,129)
         if smooth:                                                                  # :283-291
             lamda, smooth_f, frame = 0.8, 10, 149

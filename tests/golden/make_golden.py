@@ -73,7 +73,7 @@ def main():
     out = {}
 
     # ---- body pixel: wrapper end to end (config 3) ------------------------------------------
-    if want("pixel_b1_t30") or want("pixel_b3_t75") or want("pixel_cont"):
+    if want("pixel_b1_t30") or want("pixel_b3_t75") or want("pixel_cont") or want("wrapper_cont"):
         g = ref_bp.TrainWrapper(a, cfg_pixel)
         g.load_state_dict(bp_ckpt)            # demo.py:54-62 passes ckpt['generator'] = this dict
     if want("pixel_b1_t30"):
@@ -128,6 +128,30 @@ def main():
                             codes1=lat1.numpy(), noise_fp=noise_fp(noise), sampler_seed=SAMPLER_SEED + 2,
                             mfcc_seed=99)
         print("pixel_cont", lat1[:, :3].tolist())
+
+
+    if want("wrapper_cont"):
+        # wrapper-level continuity=True (smplx_body_pixel.py:244-269): 2 s prefix + remainder, features of the two
+        # chunks computed separately (get_mfcc_sepa, injected here like get_mfcc_ta above), each chunk DECODED SEPARATELY
+        # (Decoder.forward ignores pre_state, vqvae_1d.py:139-149) and concatenated.
+        f0 = synth.synth_mfcc(1, 60, seed=311)[0].transpose(0, 1).numpy()       # (60,64): 2 s at 30 fps
+        f1 = synth.synth_mfcc(1, 100, seed=312)[0].transpose(0, 1).numpy()      # (100,64)
+        ref_bp.get_mfcc_sepa = lambda *aa, **kk: (np.concatenate((f0, f1), 0), f0.shape[0])
+        torch.manual_seed(SAMPLER_SEED + 3)
+        pred = g.infer_on_audio("synthetic.wav", continuity=True, id=torch.tensor([2]), fps=30, B=2)   # (2,160,129)
+        torch.manual_seed(SAMPLER_SEED + 3)
+        n0 = draw_noise(30, 2)
+        n1 = draw_noise(50, 2)
+        # VQ wrapper continuity=True (smplx_body_vq.py:256-271): five 60-frame chunks round-tripped separately
+        gv = ref_vq.TrainWrapper(a, cfg_vq)
+        gv.load_state_dict(vq_ckpt)
+        poses = synth.synth_poses(2, 300, seed=313)
+        outv = gv.infer_on_audio(torch.zeros(2, 64, 300), initial_pose=poses, continuity=True, fps=30)   # (300, 258)
+        np.savez_compressed(os.path.join(HERE, "wrapper_cont.npz"), pred=pred[:, ::3].copy(), pred_stride=3,
+                            pred_seam=pred[:, 52:68].copy(), label=np.array([2]),
+                            noise_fp0=noise_fp(n0), noise_fp1=noise_fp(n1), sampler_seed=SAMPLER_SEED + 3,
+                            vq_out=outv[::3].copy(), vq_seam=outv[56:64].copy())
+        print("wrapper_cont", pred.shape, outv.shape)
 
     # ---- VQ roundtrip (config 2) -------------------------------------------------------------
     if want("vq_roundtrip"):

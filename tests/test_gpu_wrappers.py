@@ -81,6 +81,40 @@ def test_body_pixel_wrapper_wav_and_continuity(ckpts, tmp_path):
     assert cont.shape[0] == 1 and cont.shape[2] == 129 and np.isfinite(cont).all()
 
 
+def test_body_pixel_wrapper_continuity_golden(ckpts, tmp_path, monkeypatch):
+    """continuity=True against the reference-generated golden (tests/golden/make_golden.py --only wrapper_cont):
+    the 2 s prefix and the remainder are decoded separately (nets/smplx_body_pixel.py:262-269), so the frames on
+    both sides of the seam (rows 52..67 stored in full) must match, not just the shapes."""
+    import talkshow_b200.nets.smplx_body_pixel as bp
+
+    gold = _load("wrapper_cont")
+    cfg = _cfg("body_pixel")
+    cfg.Model.vq_path = str(tmp_path / "missing.pth")
+    g = bp.TrainWrapper(_args(), cfg)
+    g.load_vq_state_dict(ckpts["vq"])
+    g.load_state_dict(ckpts["pixel"])
+    g.noise_device = "cpu"
+    f0 = synth.synth_mfcc(1, 60, seed=311)[0].t().numpy()
+    f1 = synth.synth_mfcc(1, 100, seed=312)[0].t().numpy()
+    monkeypatch.setattr(bp, "get_mfcc_sepa", lambda *a, **k: (np.concatenate((f0, f1), 0), f0.shape[0]))
+    seed = int(gold["sampler_seed"])
+    torch.manual_seed(seed)
+    n0 = torch.stack([torch.empty(2, 2048).exponential_(1) for _ in range(30)])
+    n1 = torch.stack([torch.empty(2, 2048).exponential_(1) for _ in range(50)])
+    torch.manual_seed(seed)
+    pred = g.infer_on_audio("synthetic.wav", continuity=True, id=torch.tensor(gold["label"]), fps=30, B=2)
+    assert pred.shape == (2, 160, 129)
+    # always: the oracle's per-chunk restatement with the same noise
+    m0 = torch.from_numpy(f0.T.copy())[None].repeat(2, 1, 1)
+    m1 = torch.from_numpy(f1.T.copy())[None].repeat(2, 1, 1)
+    l0, l1, ref = O.body_infer_continuity(ckpts["pixel"], ckpts["vq"], m0, m1, torch.tensor(gold["label"]).repeat(2), n0, n1, window=18)
+    assert torch.equal(g.last_codes.cpu(), torch.cat([l0, l1], 1))
+    assert np.abs(pred - ref.numpy()).max() <= 1e-4
+    if np.allclose(gold["noise_fp0"], noise_fp(n0), rtol=0, atol=1e-9) and np.allclose(gold["noise_fp1"], noise_fp(n1), rtol=0, atol=1e-9):
+        assert np.abs(pred[:, ::int(gold["pred_stride"])] - gold["pred"]).max() <= 1e-4
+        assert np.abs(pred[:, 52:68] - gold["pred_seam"]).max() <= 1e-4
+
+
 def test_body_vq_wrapper(ckpts):
     from talkshow_b200.nets import s2g_body_vq
 
@@ -93,6 +127,12 @@ def test_body_vq_wrapper(ckpts):
     assert np.abs(out - gold["out"]).max() <= 1e-4
     ib, ih = g.encode(poses)
     assert np.array_equal(ib.cpu().numpy(), gold["idx_body"]) and np.array_equal(ih.cpu().numpy(), gold["idx_hand"])
+    # continuity=True: five 60-frame chunks round-tripped separately (nets/smplx_body_vq.py:256-271), reference golden
+    gc = _load("wrapper_cont")
+    outc = g.infer_on_audio(torch.zeros(2, 64, 300), initial_pose=synth.synth_poses(2, 300, seed=313), continuity=True, fps=30)
+    assert outc.shape == (300, 258)
+    assert np.abs(outc[::3] - gc["vq_out"]).max() <= 1e-4
+    assert np.abs(outc[56:64] - gc["vq_seam"]).max() <= 1e-4
 
 
 def test_face_wrapper(ckpts):

@@ -75,6 +75,28 @@ def test_pixel_continuity(ckpts):
     assert np.array_equal(lat1.numpy(), g["codes1"])
 
 
+def test_wrapper_continuity(ckpts):
+    """wrapper-level continuity=True goldens (body-pixel: per-chunk decode; VQ: five 60-frame chunks)."""
+    g = _load("wrapper_cont")
+    seed = int(g["sampler_seed"])
+    torch.manual_seed(seed)
+    n0 = torch.stack([torch.empty(2, 2048).exponential_(1) for _ in range(30)])
+    n1 = torch.stack([torch.empty(2, 2048).exponential_(1) for _ in range(50)])
+    if not (np.allclose(g["noise_fp0"], noise_fp(n0), rtol=0, atol=1e-9) and np.allclose(g["noise_fp1"], noise_fp(n1), rtol=0, atol=1e-9)):
+        pytest.skip("host RNG stream differs from the fixture machine")
+    m0 = synth.synth_mfcc(1, 60, seed=311).repeat(2, 1, 1)
+    m1 = synth.synth_mfcc(1, 100, seed=312).repeat(2, 1, 1)
+    label = torch.tensor(g["label"]).repeat(2)
+    _, _, pred = O.body_infer_continuity(ckpts["pixel"], ckpts["vq"], m0, m1, label, n0, n1, window=18)
+    assert pred.shape == (2, 160, 129)
+    assert np.abs(pred.numpy()[:, ::int(g["pred_stride"])] - g["pred"]).max() <= 1e-6
+    assert np.abs(pred.numpy()[:, 52:68] - g["pred_seam"]).max() <= 1e-6
+    out = O.body_vq_continuity(ckpts["vq"], synth.synth_poses(2, 300, seed=313)).numpy()
+    assert out.shape == (300, 258)
+    assert np.abs(out[::3] - g["vq_out"]).max() <= 1e-6
+    assert np.abs(out[56:64] - g["vq_seam"]).max() <= 1e-6
+
+
 def test_vq_roundtrip(ckpts):
     g = _load("vq_roundtrip")
     poses = synth.synth_poses(2, 88)
