@@ -85,16 +85,16 @@ class TrainWrapper:
             aud_feat = get_mfcc_ta(aud_fn, sr=sr, fps=fps, smlpx=True, type="mfcc", am=am)
             mfcc = torch.from_numpy(np.ascontiguousarray(aud_feat.T))[None].repeat(B, 1, 1)
         label = torch.tensor([0]) if id is None else id.reshape(-1).repeat(B)[:B] if id.numel() == 1 else id
-        return self.generate(mfcc, label).cpu().numpy()
+        return self.generate(mfcc, label, noise_fn=kwargs.get("noise_fn")).cpu().numpy()
 
-    def generate(self, aud, id, frame_num=0):
+    def generate(self, aud, id, frame_num=0, noise_fn=None):
         """tensor API (:306-326): aud [B,64,M] features, id [B] -> torch (B, F, 129) on the device.
         (The reference's version passes decode()'s tuple to torch.cat and raises; this returns the
         tensor its infer_on_audio builds.)"""
         mfcc = aud.to(torch.float32)
         B, _, M = mfcc.shape
         T = self.engine.latent_rows(M)
-        noise = self._noise(T, B)
+        noise = self._noise(T, B) if noise_fn is None else noise_fn(T, B)      # [2T,B,2048] Exp(1) draws (RNG contract)
         codes, poses = self.engine.body_generate(mfcc, id.to(torch.int64), noise)
         self.last_codes = codes
         return poses

@@ -48,6 +48,31 @@ class WholeBody:
         _, body = self.e.body_generate(mfcc, label, noise, want_codes=False)
         return self.e.assemble_pose(face, body, stand)
 
+    def generate_sharded(self, mfcc, wave, label, rank, world, noise_full=None, seed=None, stand=False, gather=True,
+                         group=None):
+        """Multi-GPU form of ``generate`` whose RESULT DOES NOT DEPEND ON ``world``: the arguments are
+        the FULL batch (host or device tensors, identical on every rank), the sampler noise is drawn for the full batch in
+        the reference's order — ``noise_full`` [2T,B,2048], or drawn here from ``seed`` on this rank's device generator
+        (same seed on every rank gives every rank the same stream) — and rank r keeps the slice of its contiguous shard
+        ``shard_range(B, r, world)``.  Each rank runs its shard; ONE all-gather rebuilds [B,F,265] everywhere."""
+        B, _, M = mfcc.shape
+        lo, hi = shard_range(B, rank, world)
+        T = self.e.latent_rows(M)
+        if noise_full is None:
+            g = None
+            if seed is not None:
+                g = torch.Generator(device=self.device)
+                g.manual_seed(int(seed))
+            noise_full = draw_sampler_noise(T, B, self.device, generator=g)
+        if hi == lo:                                                     # more ranks than samples: nothing to run here
+            frame = wave.shape[1] * 30 // 16000
+            local = torch.empty(0, frame, 265, device=self.device)
+        else:
+            dev = lambda t: t[lo:hi].to(self.device, non_blocking=True)
+            local = self.generate(dev(mfcc), dev(wave), dev(label), noise=noise_full[:, lo:hi].to(self.device).contiguous(),
+                                  stand=stand)
+        return allgather_poses(local, B, world, group=group) if gather else local
+
     def generate_host(self, mfcc_host, wave_host, label_host, out_host=None, **kw):
         """Public end-to-end call with HOST buffers (pinned for async copies): H2D inputs, generate,
         D2H result.  Returns the host tensor [B,F,265]."""
