@@ -16,7 +16,7 @@ void* ts_engine::dmalloc(size_t bytes) {
   if (host_only) return nullptr;
   void* d = nullptr;
   TS_CUDA(cudaMalloc(&d, bytes ? bytes : 16));
-  owned.push_back(d);
+  (alloc_sink ? *alloc_sink : owned).push_back(d);
   return d;
 }
 
@@ -33,8 +33,7 @@ extern "C" int ts_engine_create(ts_engine** out, int device) {
       int n = 0;
       TS_CUDA(cudaGetDeviceCount(&n));
       if (device >= n) fail(TS_ERR_INVALID, "device %d out of range (%d devices)", device, n);
-      TS_CUDA(cudaSetDevice(device));
-      cudaDeviceProp prop;
+      cudaDeviceProp prop;   // no cudaSetDevice here: creating an engine does not change the caller's current device
       TS_CUDA(cudaGetDeviceProperties(&prop, device));
       if (prop.major < 10) fail(TS_ERR_UNSUPPORTED, "talkshow_b200 needs an sm_100 (Blackwell) device, found sm_%d%d", prop.major, prop.minor);
       e->sm_count = prop.multiProcessorCount;
@@ -51,9 +50,11 @@ extern "C" int ts_engine_create(ts_engine** out, int device) {
 extern "C" void ts_engine_destroy(ts_engine* e) {
   if (!e) return;
   if (!e->host_only) {
-    cudaSetDevice(e->device);
+    ts::DeviceGuard g(e);
     cudaDeviceSynchronize();
     for (void* p : e->owned) cudaFree(p);
+    for (auto& kv : e->slot_mem)
+      for (void* p : kv.second) cudaFree(p);
     e->ws.buf.release();
   }
   delete e->pix;

@@ -131,21 +131,76 @@ struct ts_engine {
   int pixel_fusion = 1;      // plan built at ts_load_pixelcnn: 0 plain 84-stage, 1 fused 52-stage, 2 fused + vert_to_horiz in the horizontal pass
   bool tc_pair = true;       // CTA-pair (cta_group::2) 256x256 tensor-core kernel (default)
   bool tc_multicast = false;  // share operand boxes inside a thread-block cluster by TMA multicast
+  bool tc_attr_set = false;  // cudaFuncSetAttribute(max dynamic smem) of the tcgen05 kernels done on this engine's device
   bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows
   ts::PixelPlan* pix = nullptr;
   ts::ConvStacks* conv = nullptr;
   ts::FaceNet* face = nullptr;
   void* mfcc_tables = nullptr;  // ts::MfccTables (mfcc.cu)
   ts::Workspace ws;
-  std::vector<void*> owned;  // device allocations holding packed weights
+  std::vector<void*> owned;  // device allocations that live as long as the engine
+  // allocations of the weight sets, one slot per loadable module ("pixelcnn", "audioenc", "vq0", "vq1", "face"):
+  // reloading a module frees the previous set (ts::LoadScope), a failed load frees its partial uploads
+  std::map<std::string, std::vector<void*>> slot_mem;
+  std::vector<void*>* alloc_sink = nullptr;
   float* upload(const std::vector<float>& h);
   void* dmalloc(size_t bytes);
 };
 
+namespace ts {
+// Every entry point runs with the ENGINE's device current (allocations, tensor maps, launches) and restores the
+// caller's device on exit: a process may hold one engine per GPU, or call torch.cuda.set_device between calls.
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  explicit DeviceGuard(const ts_engine* e) {
+    if (!e || e->host_only) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    if (prev != e->device) {
+      if (cudaSetDevice(e->device) != cudaSuccess) ts::fail(TS_ERR_CUDA, "cudaSetDevice(%d) failed", e->device);
+      active = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (active && prev >= 0) cudaSetDevice(prev);
+  }
+};
+}  // namespace ts
+
+namespace ts {
+// Scope of one ts_load_*: every dmalloc/upload inside lands in the module's slot.  commit() (after the new module
+// object has been installed) synchronises the device and frees the slot's previous allocations; leaving the scope
+// without commit() (an exception part-way through) frees what this load had uploaded so far.
+struct LoadScope {
+  ts_engine* e;
+  std::string slot;
+  std::vector<void*> mem;
+  bool done = false;
+  LoadScope(ts_engine* e_, const char* slot_) : e(e_), slot(slot_) { e->alloc_sink = &mem; }
+  void commit() {
+    e->alloc_sink = nullptr;
+    std::vector<void*>& old = e->slot_mem[slot];
+    if (!old.empty() && !e->host_only) {
+      cudaDeviceSynchronize();
+      for (void* p : old) cudaFree(p);
+    }
+    old.swap(mem);
+    mem.clear();
+    done = true;
+  }
+  ~LoadScope() {
+    e->alloc_sink = nullptr;
+    if (!done && !e->host_only)
+      for (void* p : mem) cudaFree(p);
+  }
+};
+}  // namespace ts
+
 // run `body`, convert exceptions to status codes
 #define TS_API_BEGIN(e) \
   try {                 \
-    if (!(e)) return TS_ERR_INVALID;
+    if (!(e)) return TS_ERR_INVALID; \
+    ts::DeviceGuard _ts_device_guard(e);
 #define TS_API_END(e)                     \
   return TS_OK;                           \
   }                                       \

@@ -257,8 +257,12 @@ extern "C" int ts_load_audioenc(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
   if (!e->conv) e->conv = new ConvStacks();
-  pack_trunk(e, ck, "", 64, 256, &e->conv->audio);
+  LoadScope scope(e, "audioenc");
+  Trunk t;
+  pack_trunk(e, ck, "", 64, 256, &t);
+  e->conv->audio = t;
   e->conv->audio_loaded = true;
+  scope.commit();
   TS_API_END(e)
 }
 
@@ -267,7 +271,11 @@ extern "C" int ts_load_vq(ts_engine* e, int which, const ts_tensor* tensors, int
   if (which < 0 || which > 1) fail(TS_ERR_INVALID, "ts_load_vq: which must be 0 (body) or 1 (hand)");
   Ckpt ck(tensors, n);
   if (!e->conv) e->conv = new ConvStacks();
-  pack_vq(e, ck, &e->conv->vq[which]);
+  LoadScope scope(e, which ? "vq1" : "vq0");
+  VQNet v;
+  pack_vq(e, ck, &v);
+  e->conv->vq[which] = v;
+  scope.commit();
   TS_API_END(e)
 }
 

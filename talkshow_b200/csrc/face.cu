@@ -6,6 +6,8 @@
 // fp32 throughout (the parity bar is 1e-4 max-abs on the 103 outputs).
 #include <cuda_fp16.h>
 #include "convstack.h"
+
+#include <memory>
 #include "pixelcnn.h"
 
 namespace ts {
@@ -977,7 +979,9 @@ using namespace ts;
 extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
-  FaceNet* F = new FaceNet();
+  LoadScope scope(e, "face");
+  std::unique_ptr<FaceNet> Fp(new FaceNet());   // a throw part-way through frees the net and (scope) its uploads
+  FaceNet* F = Fp.get();
   const std::string a = "audio_encoder.";
   F->conv0_w = up(e, ck.f32(a + "feature_extractor.conv_layers.0.conv.weight", {512, 1, 10}), 5120);
   F->gn_g = up(e, ck.f32(a + "feature_extractor.conv_layers.0.layer_norm.weight", {512}), 512);
@@ -1052,7 +1056,8 @@ extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
     F->fin[br] = pack_ckc(e, ck.f32(p + "weight", {od, c, 1}), ck.f32(p + "bias", {od}), od, c, 1);
   }
   delete e->face;
-  e->face = F;
+  e->face = Fp.release();
+  scope.commit();
   TS_API_END(e)
 }
 

@@ -619,11 +619,10 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.a_hi = base_hi; P.a_lo = base_lo; P.a_rows = R;
   // whole-row L2 prefetch measured slower (96 vs 89 ms per face pass): off unless TS_TC_ROWPF=1
   { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1') ? 1 : 0; }
-  static bool attr = false;
-  if (!attr) {
+  if (!e->tc_attr_set) {   // the max-dynamic-smem attribute is per device: cached per engine, not per process
     TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-    attr = true;
+    e->tc_attr_set = true;
   }
   // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
   dim3 grid((unsigned)(((tiles_n + cn - 1) / cn) * cn), (unsigned)(((tiles_m + cm - 1) / cm) * cm));

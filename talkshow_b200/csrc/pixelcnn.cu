@@ -1434,10 +1434,12 @@ extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
   const bool clplan = e->pixel_mode == 3;   // the cluster executor knows schedules 0 and 1 only
+  LoadScope scope(e, "pixelcnn");
   PixelPlan* P = build_plan(e, ck, clplan ? std::min(e->pixel_fusion, 1) : e->pixel_fusion, clplan ? PIX_CL : 1);
   P->p2 = build_plan2(e, ck, P->L);
   delete e->pix;
   e->pix = P;
+  scope.commit();
   TS_API_END(e)
 }
 

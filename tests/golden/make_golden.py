@@ -195,6 +195,16 @@ def main():
         out = matrix_to_axis_angle(rotation_6d_to_matrix(d6))
         np.savez_compressed(os.path.join(HERE, "rot6d.npz"), d6=d6.numpy(), aa=out.numpy())
         print("rot6d", d6.shape, float(out.abs().max()), bool(torch.isfinite(out).all()))
+    # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
+    if want("options"):
+        import json
+        from trainer.options import parse_args as ref_parse_args
+        demo_cmd = ["--config_file", "./config/body_pixel.json", "--infer", "--audio_file", "./demo_audio/1st-page.wav",
+                    "--id", "2", "--whole_body", "--num_sample", "12"]
+        json.dump({"defaults": vars(ref_parse_args().parse_args([])), "demo_cmd": demo_cmd,
+                   "demo": vars(ref_parse_args().parse_args(demo_cmd))},
+                  open(os.path.join(HERE, "options.json"), "w"), indent=1, sort_keys=True)
+        print("options", len(vars(ref_parse_args().parse_args([]))))
     os.chdir(cwd)
 
 

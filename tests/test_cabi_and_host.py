@@ -11,7 +11,7 @@ import pytest
 import torch
 
 import talkshow_oracle as O
-from conftest import ROOT
+from conftest import GOLDEN, ROOT
 from talkshow_b200 import _lib, synth
 
 
@@ -88,11 +88,20 @@ def test_config_schema_matches_reference_fields():
 
 
 def test_cli_flags():
+    """parse_args() returns the PARSER like the reference (scripts/demo.py:251-252), and parses to the same namespace
+    as the reference's parser — defaults and a demo command line, fixture written by make_golden.py --only options."""
+    import argparse
+    import json
+
     from talkshow_b200.trainer.options import parse_args
 
-    a = parse_args(["--config_file", "./config/body_pixel.json", "--infer", "--audio_file", "x.wav", "--id", "2",
-                    "--num_sample", "12", "--body_model_name", "s2g_body_pixel"])
-    assert a.infer and a.id == 2 and a.num_sample == 12 and a.gpu == 0 and a.audio_file == "x.wav"
+    gold = json.load(open(os.path.join(GOLDEN, "options.json")))
+    parser = parse_args()
+    assert isinstance(parser, argparse.ArgumentParser)
+    assert vars(parser.parse_args([])) == gold["defaults"]
+    assert vars(parse_args().parse_args(gold["demo_cmd"])) == gold["demo"]
+    a = parse_args().parse_args(["--infer", "--audio_file", "x.wav", "--id", "2", "--num_sample", "12"])
+    assert a.infer and a.id == 2 and a.num_sample == 12 and a.gpu == 0 and a.body_model_name == "s2g_body_pixel"
 
 
 def test_pose_layout_helpers():
