@@ -57,7 +57,7 @@ extern "C" void ts_engine_destroy(ts_engine* e) {
       for (void* p : kv.second) cudaFree(p);
     e->ws.buf.release();
   }
-  delete e->pix;
+  ts::pixel_destroy(e);
   delete e->conv;
   ts::face_destroy(e);
   ts::mfcc_destroy(e);
@@ -68,7 +68,7 @@ extern "C" const char* ts_last_error(ts_engine* e) { return e ? e->err.c_str() :
 extern "C" int ts_engine_sm_count(ts_engine* e) { return e ? e->sm_count : 0; }
 extern "C" int64_t ts_launch_count(ts_engine* e) { return e ? e->launches : 0; }
 extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
-  if (!e || mode < 0 || mode > 3) return TS_ERR_INVALID;
+  if (!e || mode < 0 || mode > 2) return TS_ERR_INVALID;
   e->pixel_mode = mode;
   return TS_OK;
 }

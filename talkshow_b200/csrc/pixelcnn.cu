@@ -15,6 +15,7 @@
 #include "convstack.h"
 
 #include <algorithm>
+#include <memory>
 #include <cmath>
 
 namespace ts {
@@ -22,7 +23,6 @@ namespace ts {
 // =============================================================================================
 // host: plan construction
 // =============================================================================================
-static int pixc_max_clusters();   // resident PIX_CL-CTA clusters of the cluster-plan executor on the current device
 
 struct Job {
   int epi, layer, col, nrows, K, ncol;
@@ -33,8 +33,7 @@ struct Job {
 // (W_next (W_res g + b + x) = (W_next W_res) g + W_next b + W_next x), the layer-0 gate of column 0 (no
 // matmul) rides in the last vertical stage, and the layer-0 gate of column 1 is a table lookup done by the
 // sampler itself: 16 + 2 x 18 = 52 dependent stages per row instead of 84.
-static std::vector<std::vector<Job>> build_stages_fused(int L) {
-  const int D = PIX_D;
+static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D) {
   std::vector<std::vector<Job>> st;
   st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
   st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});
@@ -63,8 +62,7 @@ static std::vector<std::vector<Job>> build_stages_fused(int L) {
 // difference being the 49 CTAs that vert_to_horiz of the previous layer occupies.  Its output is consumed only by the
 // horizontal pass of the same row, so here it runs per column (EPI_V2H1) beside the horizontal stage that precedes
 // its consumer; the pre-gate vertical outputs (HV) get one slot per layer instead of a 2-deep ring.
-static std::vector<std::vector<Job>> build_stages_fused2(int L) {
-  const int D = PIX_D;
+static std::vector<std::vector<Job>> build_stages_fused2(int L, int D = PIX_D) {
   std::vector<std::vector<Job>> st;
   st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
   st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});   // layer 0: needed by both layer-0 gates
@@ -92,8 +90,7 @@ static std::vector<std::vector<Job>> build_stages_fused2(int L) {
   return st;
 }
 
-static std::vector<std::vector<Job>> build_stages(int L) {
-  const int D = PIX_D;
+static std::vector<std::vector<Job>> build_stages(int L, int D = PIX_D) {
   std::vector<std::vector<Job>> st;
   // ---- vertical pass -----------------------------------------------------------------------
   st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
@@ -144,6 +141,7 @@ static PixLayout make_layout(int L, int hvslots) {
 struct WeightSrc {
   const Ckpt& ck;
   int L;
+  int D;   // hidden width (256; 512 for the convert_to_6d geometry)
   std::vector<const float*> vs, vsb, v2h, v2hb, hs, hsb, hr, hrb;
   const float *fv, *fh, *o1, *o1b, *o2, *o2b;
   // fused plan: products of adjacent linear maps, accumulated in fp64 and rounded once
@@ -168,14 +166,12 @@ struct WeightSrc {
     }
   }
   void build_fused() {
-    const int D = PIX_D;
     Mh.resize(L); bh.resize(L);
     for (int l = 2; l < L; ++l) compose(hs[l] + 1, 2 * D, 2, 2 * D, hr[l - 1], hrb[l - 1], D, Mh[l], bh[l]);
     compose(fh, 2 * D, 1, D, hr[0], hrb[0], D, Mf, bf);
     compose(o1, D, 1, 512, hr[L - 1], hrb[L - 1], D, Mo, bo);
   }
-  WeightSrc(const Ckpt& c, int L_) : ck(c), L(L_) {
-    const int D = PIX_D;
+  WeightSrc(const Ckpt& c, int L_, int D_ = PIX_D) : ck(c), L(L_), D(D_) {
     for (int l = 0; l < L; ++l) {
       std::string p = "layers." + std::to_string(l) + ".";
       vs.push_back(ck.f32(p + "vert_stack.weight", {2 * D, D, l == 0 ? 4 : 2, 3}));
@@ -194,9 +190,8 @@ struct WeightSrc {
     o2 = ck.f32("output_conv.2.weight", {PIX_NCODE, 512, 1, 1});
     o2b = ck.f32("output_conv.2.bias", {PIX_NCODE});
   }
-  static int chan(const Job& j, int jr) { return j.pairs ? (jr & 1) * PIX_D + (jr >> 1) : jr; }
+  int chan(const Job& j, int jr) const { return j.pairs ? (jr & 1) * D + (jr >> 1) : jr; }
   float w(const Job& j, int jr, int k) const {
-    const int D = PIX_D;
     int ch = chan(j, jr), sidx = k / D, ci = k % D, l = j.layer;
     switch (j.epi) {
       case EPI_VERT0: {  // seg = kh*2 + input col; kw = input col - out col + 1   (Appendix C of SURVEY.md)
@@ -256,7 +251,30 @@ static Layer pack_1x1(ts_engine* e, const float* w, int ldw, int koff, const flo
   return L;
 }
 
-static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
+// parts of the plan shared by the executors: algorithmic bytes per row and the audio-term layers
+static void plan_common(ts_engine* e, const Ckpt& ck, PixelPlan* P, int L, int D) {
+  // algorithmic bytes per row (SURVEY.md §8d): every dense PixelCNN weight + bias once — unique
+  // weights, i.e. without the duplication of the shared kw=1 vertical tap across the two output
+  // columns and without the row padding of the staged blob; mask-A-zeroed taps and the gathered
+  // tables (code embedding, class embedding) excluded.
+  int64_t w = 0;
+  for (int l = 0; l < L; ++l) {
+    w += (int64_t)2 * D * D * (l == 0 ? 3 : 2) * 3 + 2 * D;   // vert_stack (layer 0: masked row dropped)
+    w += (int64_t)2 * D * 2 * D + 2 * D;                      // vert_to_horiz
+    w += (int64_t)2 * D * D * (l == 0 ? 1 : 2) + 2 * D;       // horiz_stack (layer 0: masked tap dropped)
+    w += (int64_t)D * D + D;                                  // horiz_resid
+  }
+  w += 2 * ((int64_t)D * 2 * D + D) + ((int64_t)D * 256 + D);  // fusion_v, fusion_h, embedding_aud
+  w += (int64_t)512 * D + 512 + (int64_t)PIX_NCODE * 512 + PIX_NCODE;
+  P->row_bytes = 4 * w;
+  // audio terms: a = embedding_aud(aud); AUDV = fusion_v[:, D:]*a + b_v; AUDH = fusion_h[:, D:]*a + b_h
+  P->emb_aud = pack_1x1(e, ck.f32("embedding_aud.weight", {D, 256, 1, 1}), 256, 0, ck.f32("embedding_aud.bias", {D}), D, 256);
+  P->fuse_v_a = pack_1x1(e, ck.f32("fusion_v.weight", {D, 2 * D, 1, 1}), 2 * D, D, ck.f32("fusion_v.bias", {D}), D, D);
+  P->fuse_h_a = pack_1x1(e, ck.f32("fusion_h.weight", {D, 2 * D, 1, 1}), 2 * D, D, ck.f32("fusion_h.bias", {D}), D, D);
+}
+
+static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
+  const int cl = 1;   // CTAs per work unit
   const int D = PIX_D;
   const ts_tensor* emb = ck.get("embedding.weight");
   if (emb->ndim != 2 || emb->shape[1] != D || emb->shape[0] != PIX_NCODE)
@@ -276,13 +294,6 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
     if (n >= PIX_MB && n <= e->sm_count) P->ncta = n;
   }
   P->cl = cl;
-  if (cl > 1) {
-    // cluster plan (experimental, ts_set_pixelcnn_mode(3) before the load): the unit of work is a cluster of `cl`
-    // CTAs that share a task's output rows and split its K range; B200 keeps 132 CTAs of 4-CTA clusters resident
-    // (B300_MICROARCH.md, CTAS_ACTIVE at cluster size 4), i.e. 33 clusters on 148 SMs
-    const int ncl = e->host_only ? (e->sm_count * 33) / 148 : pixc_max_clusters();
-    P->ncta = std::min(e->sm_count / cl, ncl) * cl;
-  }
   P->nclasses = ncls;
   bool fused = level >= 1 && L >= 3;
   P->sched = fused ? level : 0;
@@ -334,7 +345,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
     std::vector<int> nc(jobs.size()), lo(jobs.size());
     int used = 0;
     const int nunit = P->ncta / cl;                    // work units of a stage: CTAs, or clusters of the cluster plan
-    const int rowcap = cl > 1 ? PIX_CMAXROWS : PIX_MAXROWS;
+    const int rowcap = PIX_MAXROWS;
     for (size_t i = 0; i < jobs.size(); ++i) {
       const int cap = jobs[i].K ? rowcap : 4 * PIX_MAXROWS;  // matmul rows per unit; epilogue-only tasks: 64
       lo[i] = (jobs[i].nrows + cap - 1) / cap;
@@ -380,29 +391,9 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level, int cl) {
       }
     }
   }
-  // algorithmic bytes per row (SURVEY.md §8d): every dense PixelCNN weight + bias once — unique
-  // weights, i.e. without the duplication of the shared kw=1 vertical tap across the two output
-  // columns and without the row padding of the staged blob; mask-A-zeroed taps and the gathered
-  // tables (code embedding, class embedding) excluded.
-  {
-    int64_t w = 0;
-    for (int l = 0; l < L; ++l) {
-      w += (int64_t)2 * D * D * (l == 0 ? 3 : 2) * 3 + 2 * D;   // vert_stack (layer 0: masked row dropped)
-      w += (int64_t)2 * D * 2 * D + 2 * D;                      // vert_to_horiz
-      w += (int64_t)2 * D * D * (l == 0 ? 1 : 2) + 2 * D;       // horiz_stack (layer 0: masked tap dropped)
-      w += (int64_t)D * D + D;                                  // horiz_resid
-    }
-    w += 2 * ((int64_t)D * 2 * D + D) + ((int64_t)D * 256 + D);  // fusion_v, fusion_h, embedding_aud
-    w += (int64_t)512 * D + 512 + (int64_t)PIX_NCODE * 512 + PIX_NCODE;
-    P->row_bytes = 4 * w;
-  }
   P->staged_row_bytes = 4 * ((int64_t)(P->blob.size() - table_floats) + 3LL * D * D);
   (void)dense;
-
-  // audio terms: a = embedding_aud(aud); AUDV = fusion_v[:, D:]*a + b_v; AUDH = fusion_h[:, D:]*a + b_h
-  P->emb_aud = pack_1x1(e, ck.f32("embedding_aud.weight", {D, 256, 1, 1}), 256, 0, ck.f32("embedding_aud.bias", {D}), D, 256);
-  P->fuse_v_a = pack_1x1(e, ws.fv, 2 * D, D, ck.f32("fusion_v.bias", {D}), D, D);
-  P->fuse_h_a = pack_1x1(e, ws.fh, 2 * D, D, ck.f32("fusion_h.bias", {D}), D, D);
+  P->has_v1 = true;
 
   if (!e->host_only) {
     P->d_table = (PixTask*)e->dmalloc(P->table.size() * sizeof(PixTask));
@@ -1025,250 +1016,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
   }
 }
 
-// =============================================================================================
-// EXPERIMENTAL cluster plan executor (ts_set_pixelcnn_mode(3) before ts_load_pixelcnn)
-// =============================================================================================
-// Same stage table, same epilogues, same grid barrier as pixelcnn_kernel.  The unit of work is a cluster of
-// PIX_CL = 4 CTAs: the four CTAs share the task's output rows (up to 64) and each owns a quarter of its K
-// range, so a CTA reads a quarter of the stage's [K][64] activation slab (the whole K/32 slice of a warp sits
-// in registers, one load burst per stage) and stages the same number of weight bytes as before.  Partial
-// sums are reduced across the 8 warps in shared memory, exchanged between the four CTAs through distributed
-// shared memory (mapa + ld.shared::cluster behind a cluster barrier) and summed in rank order; the epilogue
-// items of the task are striped over the four CTAs.
-constexpr size_t PIXC_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB + PIX_CMAXROWS * PIX_MB) * sizeof(float) + 64 +
-                             PIX_MAXSTAGES * sizeof(PixTask);
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_id_x() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t rank) {
-  uint32_t ra;
-  float v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
-}
-
-// partial products of rows [rowofs, rowofs + 4 RC) over the warp's register-resident K slice (ng groups of 8 rows)
-template <int RC>
-__device__ __forceinline__ void mm_rows_cl(const float* __restrict__ Wsm, int rpad, int rowofs, int ng, int kloc0,
-                                           const unsigned long long (&x)[6][8], float* red, int slice, int lane) {
-  unsigned long long acc[4 * RC];
-#pragma unroll
-  for (int j = 0; j < 4 * RC; ++j) acc[j] = 0ull;
-#pragma unroll
-  for (int g = 0; g < 6; ++g) {
-    if (g < ng) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4* w4 = reinterpret_cast<const float4*>(Wsm + (size_t)(kloc0 + g * 8 + u) * rpad + rowofs);
-#pragma unroll
-        for (int rc = 0; rc < RC; ++rc) {
-          const float4 w = w4[rc];
-          fma2(acc[rc * 4 + 0], w.x, x[g][u]);
-          fma2(acc[rc * 4 + 1], w.y, x[g][u]);
-          fma2(acc[rc * 4 + 2], w.z, x[g][u]);
-          fma2(acc[rc * 4 + 3], w.w, x[g][u]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4 * RC; ++j)
-    *reinterpret_cast<unsigned long long*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
-}
-
-__device__ void run_matmul_task_cl(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, float* xbuf,
-                                   uint32_t rank, uint32_t clid) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const PixLayout& a = A.lay;
-  const int npass = (t.epi == EPI_V2H || t.epi == EPI_FUSEV) ? 2 : 1;
-  const int Ks = t.K / PIX_CL;                 // this CTA's K range is [rank * Ks, rank * Ks + Ks)
-  const float* bias = Wsm + (size_t)Ks * t.rpad;
-  float* arena = A.arena;
-  const uint32_t xaddr = smem_u32(xbuf);
-  for (int pass = 0; pass < npass; ++pass) {
-    int s_seg[6];
-    resolve_segments(t, pass, r, a, A.L, s_seg);
-    if (pass > 0) cluster_sync_all();          // the peers finished reading this CTA's partials of the previous pass
-    if (t.K > 0) {
-      const int kper = Ks >> 3, ng = kper >> 3;  // warp slice: K/32 rows = K/256 groups of 8 (1, 2, 3, 4 or 6)
-      const int slice = (warp + (int)clid) & 7;
-      const int kloc0 = slice * kper, kglob0 = (int)rank * Ks + kloc0;
-      unsigned long long x[6][8];
-#pragma unroll
-      for (int g = 0; g < 6; ++g) {
-        if (g < ng) {
-          const int k = kglob0 + g * 8;
-          const float* base = arena + s_seg[k >> 8] + ((k & 255) << 6) + lane * 2;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * PIX_MB));
-        }
-      }
-      for (int rp = 0; rp * 16 < t.rpad; ++rp) {
-        const int rcp = min(4, (t.rpad - rp * 16) >> 2);
-        switch (rcp) {
-          case 1: mm_rows_cl<1>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
-          case 2: mm_rows_cl<2>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
-          case 3: mm_rows_cl<3>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
-          default: mm_rows_cl<4>(Wsm, t.rpad, rp * 16, ng, kloc0, x, red, slice, lane); break;
-        }
-        __syncthreads();
-        for (int it = tid; it < 4 * rcp * PIX_MB; it += PIX_THREADS)
-          xbuf[(rp * 16 + (it >> 6)) * PIX_MB + (it & (PIX_MB - 1))] = red_sum(red, it >> 6, it & (PIX_MB - 1));
-        __syncthreads();
-      }
-      cluster_sync_all();                      // all four partial tiles are complete and visible cluster-wide
-    }
-    auto csum = [&](int row, int m) -> float {   // fixed rank order -> deterministic
-      if (t.K == 0) return 0.f;
-      const uint32_t ad = xaddr + (uint32_t)(row * PIX_MB + m) * 4u;
-      return ((ld_dsmem(ad, 0) + ld_dsmem(ad, 1)) + ld_dsmem(ad, 2)) + ld_dsmem(ad, 3);
-    };
-    const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE || t.epi == EPI_HGATE2);
-    const int items = (pairs ? t.nrows >> 1 : t.nrows) * PIX_MB;
-    for (int it = (int)rank * PIX_THREADS + tid; it < items; it += PIX_CL * PIX_THREADS) {   // items striped over the 4 CTAs
-      const int m = it & (PIX_MB - 1), j = it >> 6;
-      if (pairs) {
-        const int q = (t.row0 >> 1) + j;  // gate channel
-        float at = csum(2 * j, m) + bias[2 * j];
-        float as = csum(2 * j + 1, m) + bias[2 * j + 1];
-        const float* cls = arena + a.CLS + (t.layer * 2) * PIX_SEG;
-        float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
-        if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
-          const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
-          float vt = __ldcg(v2h + q * PIX_MB + m);
-          float vs = __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
-          float zt = (vt + at) + ct;
-          float zs = (vs + as) + cs;
-          arena[a.G + (t.layer & 1) * PIX_SEG + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
-        } else {
-          float* hv = arena + a.HV + (((t.layer & 1) * 2 + t.col) * 2) * PIX_SEG;
-          hv[q * PIX_MB + m] = at;
-          hv[(PIX_D + q) * PIX_MB + m] = as;
-          float g = tanhf(at + ct) * sigmoidf_(as + cs);
-          if (t.epi == EPI_VERT0) arena[a.XV1P + t.col * PIX_SEG + q * PIX_MB + m] = g;
-          else if (t.layer + 1 < A.L)
-            arena[a.XV + (((t.layer + 1) * 2 + (r & 1)) * 2 + t.col) * PIX_SEG + q * PIX_MB + m] = g;
-        }
-      } else {
-        const int ch = t.row0 + j;
-        float v = csum(j, m) + bias[j];
-        switch (t.epi) {
-          case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * PIX_SEG + ch * PIX_MB + m] = v; break;
-          case EPI_FUSEV: {
-            float au = m < A.B ? A.audv[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
-            arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * PIX_SEG + ch * PIX_MB + m] = v + au;
-          } break;
-          case EPI_HRES:
-            if (t.layer == 0) arena[a.XHP + ch * PIX_MB + m] = v;
-            else {
-              float xh = __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
-              arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
-            }
-            break;
-          case EPI_FUSEH: case EPI_HRESF: {
-            float au = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
-            arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
-          } break;
-          case EPI_OUT1: case EPI_OUT1F: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
-          case EPI_OUT2: arena[a.LOG + ch * PIX_MB + m] = v; break;
-        }
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_cl_kernel(PixArgs A) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* wbuf = reinterpret_cast<float*>(smem_raw);
-  float* red = wbuf + 2 * PIX_WBUF;
-  float* xbuf = red + 8 * PIX_MAXROWS * PIX_MB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + PIX_CMAXROWS * PIX_MB);
-  PixTask* tasks = reinterpret_cast<PixTask*>(bars + 8);
-  const int tid = threadIdx.x, cta = blockIdx.x;
-  const uint32_t rank = cluster_ctarank(), clid = cluster_id_x();
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < A.nstages * 8; i += PIX_THREADS)
-    reinterpret_cast<int*>(tasks)[i] = reinterpret_cast<const int*>(A.table + (size_t)(i >> 3) * A.ncta + cta)[i & 7];
-  __syncthreads();
-  cluster_sync_all();                           // every CTA of the cluster is running before any DSMEM access
-  auto tbytes = [](const PixTask& t) { return (uint32_t)((t.K / PIX_CL + 1) * t.rpad) * 4u; };
-  uint32_t uses[2] = {0u, 0u};
-  const int total = A.Ttot * A.nstages;
-  if (tid == 0) {
-    const PixTask t0 = tasks[0];
-    if (task_active(t0, 0, A.log_r0) && t0.epi != EPI_SAMPLE) {
-      mbar_expect_tx(&bars[0], tbytes(t0));
-      tma_load_1d(wbuf, A.blob + t0.wofs, tbytes(t0), &bars[0]);
-    }
-  }
-  int r = 0, s = 0;
-  for (int g = 0; g < total; ++g) {
-    const PixTask t = tasks[s];
-    const int buf = g & 1;
-    if (tid == 0 && g + 1 < total) {
-      int s1 = s + 1, r1 = r;
-      if (s1 == A.nstages) { s1 = 0; r1 = r + 1; }
-      const PixTask tn = tasks[s1];
-      if (task_active(tn, r1, A.log_r0) && tn.epi != EPI_SAMPLE) {
-        fence_proxy_async();
-        mbar_expect_tx(&bars[buf ^ 1], tbytes(tn));
-        tma_load_1d(wbuf + (buf ^ 1) * PIX_WBUF, A.blob + tn.wofs, tbytes(tn), &bars[buf ^ 1]);
-      }
-    }
-    const bool active = task_active(t, r, A.log_r0);   // identical for the four CTAs of a cluster
-    const bool has_w = active && t.epi != EPI_SAMPLE;
-    if (has_w) { mbar_wait(&bars[buf], uses[buf] & 1u); uses[buf]++; }
-    if (g > 0) grid_wait(A.barrier, (unsigned)g * (unsigned)A.ncta);
-    if (active) {
-      if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
-      else run_matmul_task_cl(t, A, r, wbuf + buf * PIX_WBUF, red, xbuf, rank, clid);
-    }
-    grid_arrive(A.barrier);
-    if (++s == A.nstages) { s = 0; ++r; }
-  }
-  cluster_sync_all();                           // no CTA leaves while a peer may still read its shared memory
-}
-
-static void pixc_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int ncta, cudaStream_t s) {
-  cfg = cudaLaunchConfig_t{};
-  cfg.gridDim = dim3(ncta);
-  cfg.blockDim = dim3(PIX_THREADS);
-  cfg.dynamicSmemBytes = PIXC_SMEM;
-  cfg.stream = s;
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = PIX_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  at[1].id = cudaLaunchAttributeCooperative;
-  at[1].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 2;
-}
-static int pixc_max_clusters() {
-  TS_CUDA(cudaFuncSetAttribute(pixelcnn_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIXC_SMEM));
-  cudaLaunchConfig_t cfg;
-  cudaLaunchAttribute at[2];
-  pixc_config(cfg, at, PIX_CL, nullptr);
-  int maxcl = 0;
-  TS_CUDA(cudaOccupancyMaxActiveClusters(&maxcl, pixelcnn_cl_kernel, &cfg));
-  return maxcl;
-}
-
-#include "pixelcnn2.inc"
+#include "pixelcnn3.inc"
 
 __global__ void build_cls_kernel(const float* __restrict__ cls_w, const int64_t* __restrict__ label, float* arena, int cls_off,
                                  int L, int ncls, int B) {
@@ -1317,54 +1065,36 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
                            int64_t* idx_out, float* logits_out, int B, int T, const int64_t* pre, int T0, cudaStream_t s,
                            bool logits_all) {
   PixelPlan* P = e->pix;
-  const int Ttot = T0 + T;
-  // audio terms for all rows of this chunk: three 256x256 GEMMs over B*Ttot rows
-  float* a_emb = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
-  float* audv = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
-  float* audh = e->ws.alloc<float>((size_t)B * Ttot * PIX_D);
-  const int nclusters = (B + C2_MB - 1) / C2_MB;
-  float* arena2 = (e->pixel_mode == 2 && P->p2) ? e->ws.alloc<float>((size_t)nclusters * ((Plan2*)P->p2)->lay.total) : nullptr;
+  Plan3* Q = (Plan3*)P->p3;
+  const int Ttot = T0 + T, D = P->D;
+  const bool v3 = e->pixel_mode == 2 || !P->has_v1;
+  // audio terms for all rows of this chunk: three GEMMs over B*Ttot rows
+  float* a_emb = e->ws.alloc<float>((size_t)B * Ttot * D);
+  float* audv = e->ws.alloc<float>((size_t)B * Ttot * D);
+  float* audh = e->ws.alloc<float>((size_t)B * Ttot * D);
+  const int MB3 = v3 ? c3_pick_mb(Q, B) : 0;
+  float* arena3 = v3 ? e->ws.alloc<float>((size_t)((B + MB3 - 1) / MB3) * make_layout3(Q->L, Q->D, MB3).total) : nullptr;
   if (e->ws.sizing) return;
   GemmP g;
   g.A = aud.row(b0, 0); g.W = P->emb_aud.W; g.bias = P->emb_aud.bias; g.C = a_emb;
-  g.M = B * Ttot; g.N = PIX_D; g.K = 256; g.mper = Ttot; g.a_bs = aud.bstride(); g.a_rs = aud.C; g.kc = 256; g.a_ts = 256;
-  g.c_bs = (long)Ttot * PIX_D; g.c_rs = PIX_D; g.ldw = 256;
+  g.M = B * Ttot; g.N = D; g.K = 256; g.mper = Ttot; g.a_bs = aud.bstride(); g.a_rs = aud.C; g.kc = 256; g.a_ts = 256;
+  g.c_bs = (long)Ttot * D; g.c_rs = D; g.ldw = 256;
   launch_gemm(e, g, s);
   GemmP h;
   h.A = a_emb; h.W = P->fuse_v_a.W; h.bias = P->fuse_v_a.bias; h.C = audv;
-  h.M = B * Ttot; h.N = PIX_D; h.K = PIX_D; h.mper = Ttot; h.a_bs = (long)Ttot * PIX_D; h.a_rs = PIX_D; h.kc = PIX_D; h.a_ts = PIX_D;
-  h.c_bs = (long)Ttot * PIX_D; h.c_rs = PIX_D; h.ldw = PIX_D;
+  h.M = B * Ttot; h.N = D; h.K = D; h.mper = Ttot; h.a_bs = (long)Ttot * D; h.a_rs = D; h.kc = D; h.a_ts = D;
+  h.c_bs = (long)Ttot * D; h.c_rs = D; h.ldw = D;
   launch_gemm(e, h, s);
   h.W = P->fuse_h_a.W; h.bias = P->fuse_h_a.bias; h.C = audh;
   launch_gemm(e, h, s);
+  (void)noise_B;
 
-  if (e->pixel_mode == 2) {
-    // v2: one 16-CTA cluster per 8 samples, no grid barrier (pixelcnn2.inc)
-    Plan2* Q = (Plan2*)P->p2;
-    Pix2Args A2;
-    A2.jobs = Q->d_jobs; A2.njobs = Q->d_njobs; A2.chunks = Q->d_chunks; A2.blob = Q->d_blob; A2.bias = Q->d_bias;
-    A2.arena = arena2; A2.emb = P->d_emb; A2.cls_w = P->d_cls; A2.audv = audv; A2.audh = audh; A2.noise = noise; A2.label = label;
-    A2.pre = pre; A2.idx_out = idx_out; A2.logits_out = logits_out; A2.lay = Q->lay; A2.rank_stride = Q->rank_stride;
-    A2.B = B; A2.T0 = T0; A2.Ttot = Ttot; A2.log_r0 = logits_all ? 0 : T0; A2.L = P->L; A2.nstages = Q->nstages;
-    A2.nchunks_row = Q->nchunks_row; A2.ncls = P->nclasses;
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2_SMEM));
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn2_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(nclusters * C2_CL);
-    cfg.blockDim = dim3(C2_THREADS);
-    cfg.dynamicSmemBytes = C2_SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = C2_CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
-    TS_CUDA(cudaLaunchKernelEx(&cfg, pixelcnn2_kernel, A2));
-    if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
-    e->launches++;
+  if (v3) {   // cluster-resident executor (pixelcnn3.inc): any batch size, clusters of 16 CTAs per 4 / 8 samples
+    launch_pixelcnn3(e, P, Q, audv, audh, label, noise, idx_out, logits_out, B, T0, Ttot, pre, logits_all, arena3, MB3, s);
     return;
   }
+  if (B > PIX_MB)
+    fail(TS_ERR_UNSUPPORTED, "pixelcnn: the grid-wide executor takes %d samples per call (got %d); the host shim chunks larger batches", PIX_MB, B);
   TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)P->lay.total * sizeof(float), s));
   TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 4096, s));
   build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, P->lay.CLS, P->L, P->nclasses, B);
@@ -1378,22 +1108,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
   A.fused = P->fused ? 1 : 0;
   A.trace = P->d_trace; A.trace_row = P->trace_row;
-  (void)noise_B;
-  if (P->cl > 1) {
-    if (e->pixel_mode == 1) fail(TS_ERR_UNSUPPORTED, "pixelcnn: the cluster plan has no per-stage debug mode");
-    TS_CUDA(cudaFuncSetAttribute(pixelcnn_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIXC_SMEM));
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute at[2];
-    pixc_config(cfg, at, P->ncta, s);
-    int maxcl = 0;
-    TS_CUDA(cudaOccupancyMaxActiveClusters(&maxcl, pixelcnn_cl_kernel, &cfg));
-    if (maxcl * PIX_CL < P->ncta)
-      fail(TS_ERR_UNSUPPORTED, "pixelcnn cluster plan: %d CTAs planned, only %d clusters of %d can be resident", P->ncta, maxcl, PIX_CL);
-    if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
-    TS_CUDA(cudaLaunchKernelEx(&cfg, pixelcnn_cl_kernel, A));
-    if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
-    e->launches++;
-  } else if (e->pixel_mode == 0 || e->pixel_mode == 3) {
+  if (e->pixel_mode == 0) {
     // A/B switch: 0 = burst loads + scalar FFMA, 4 = pipelined loads + scalar FFMA, 5 (default) = pipelined loads + FFMA2
     static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 5;
     void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : pipe == 4 ? (void*)pixelcnn_kernel<true, 4> : (void*)pixelcnn_kernel<true, 5>;
@@ -1418,11 +1133,16 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   }
 }
 
+void pixel_destroy(ts_engine* e) {
+  if (!e->pix) return;
+  delete (Plan3*)e->pix->p3;
+  delete e->pix;
+  e->pix = nullptr;
+}
+
 void pixelcnn_generate_act(ts_engine* e, const Act3& aud, const int64_t* label, const float* noise, int64_t* idx_out,
                            float* logits_out, int B, int T, const int64_t* pre, int T0, cudaStream_t s, bool logits_all) {
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
-  if (B > PIX_MB && e->pixel_mode != 2)
-    fail(TS_ERR_UNSUPPORTED, "pixelcnn: batch tile is %d samples per call (got %d); the host shim chunks larger batches", PIX_MB, B);
   generate_chunk(e, aud, 0, label, noise, B, idx_out, logits_out, B, T, pre, T0, s, logits_all);
 }
 
@@ -1433,18 +1153,35 @@ using namespace ts;
 extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   TS_API_BEGIN(e)
   Ckpt ck(tensors, n);
-  const bool clplan = e->pixel_mode == 3;   // the cluster executor knows schedules 0 and 1 only
+  const ts_tensor* emb = ck.get("embedding.weight");
+  if (emb->ndim != 2 || emb->shape[0] != PIX_NCODE)
+    fail(TS_ERR_UNSUPPORTED, "pixelcnn: embedding.weight must be [%d, dim]", PIX_NCODE);
+  const int D = (int)emb->shape[1];
+  int L = 0;
+  while (ck.has("layers." + std::to_string(L) + ".vert_stack.weight")) ++L;
+  if (L < 3 || L > 30) fail(TS_ERR_MISSING, "pixelcnn: %d layers found", L);
+  const int ncls = (int)ck.get("layers.0.class_cond_embedding.weight")->shape[0];
   LoadScope scope(e, "pixelcnn");
-  PixelPlan* P = build_plan(e, ck, clplan ? std::min(e->pixel_fusion, 1) : e->pixel_fusion, clplan ? PIX_CL : 1);
-  P->p2 = build_plan2(e, ck, P->L);
-  delete e->pix;
-  e->pix = P;
+  // the grid-wide executor (modes 0 / 1) is built for the shipped geometry dim = 256 only; every geometry runs on the
+  // cluster-resident executor (mode 2)
+  std::unique_ptr<PixelPlan> P(D == PIX_D ? build_plan(e, ck, e->pixel_fusion) : new PixelPlan());
+  P->L = L; P->D = D; P->nclasses = ncls;
+  plan_common(e, ck, P.get(), L, D);
+  Plan3* Q = build_plan3(e, ck, L, D, ncls);
+  P->p3 = Q;
+  if (!P->has_v1) { P->nstages = Q->nstages; P->ncta = C3_CL; }
+  pixel_destroy(e);
+  e->pix = P.release();
   scope.commit();
   TS_API_END(e)
 }
 
 extern "C" int64_t ts_pixelcnn_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->row_bytes : 0; }
-extern "C" int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->staged_row_bytes : 0; }
+extern "C" int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e) {
+  if (!e || !e->pix) return 0;
+  if (e->pixel_mode == 2 || !e->pix->has_v1) return (int64_t)((Plan3*)e->pix->p3)->rank_stride * C3_CL * 4;
+  return e->pix->staged_row_bytes;
+}
 
 // CUDA-event timing of the persistent kernel on its launch stream (bench.py roofline leg).
 extern "C" int ts_pixelcnn_timing(ts_engine* e, int enable) {
@@ -1475,7 +1212,7 @@ extern "C" int ts_pixelcnn_trace(ts_engine* e, int row) {
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
   if (e->host_only) fail(TS_ERR_UNSUPPORTED, "host-only engine cannot execute");
   PixelPlan* P = e->pix;
-  const size_t n = (size_t)P->nstages * P->ncta * 4;
+  const size_t n = (size_t)P->nstages * std::max(P->ncta, 16) * 4;
   if (row >= 0 && !P->d_trace) P->d_trace = (unsigned long long*)e->dmalloc(n * sizeof(unsigned long long));
   if (row >= 0) TS_CUDA(cudaMemset(P->d_trace, 0, n * sizeof(unsigned long long)));
   P->trace_row = row;
@@ -1486,7 +1223,7 @@ extern "C" int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len)
   TS_API_BEGIN(e)
   if (!e->pix || !e->pix->d_trace) fail(TS_ERR_NOT_LOADED, "pixelcnn trace not armed");
   PixelPlan* P = e->pix;
-  const int64_t n = (int64_t)P->nstages * P->ncta * 4;
+  const int64_t n = (int64_t)P->nstages * std::max(P->ncta, 16) * 4;
   if (out) {
     if (*len < n) fail(TS_ERR_INVALID, "trace buffer too small");
     TS_CUDA(cudaDeviceSynchronize());

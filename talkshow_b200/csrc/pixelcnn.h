@@ -12,8 +12,6 @@ constexpr int PIX_THREADS = 256;
 constexpr int PIX_MAXROWS = 16; // weight rows one CTA handles per stage
 constexpr int PIX_WBUF = 18560; // floats per weight staging buffer (74.2 KB), two buffers
 constexpr int PIX_NCODE = 2048;
-constexpr int PIX_CL = 4;        // cluster plan: CTAs per cluster (K split 4 ways, DSMEM reduction)
-constexpr int PIX_CMAXROWS = 64; // cluster plan: weight rows one cluster handles per stage
 
 enum PixEpi {
   EPI_IDLE = 0,
@@ -46,7 +44,9 @@ struct PixLayout {  // arena offsets in floats
 
 struct PixelPlan {
   int L = 0, ncta = 0, nstages = 0, nclasses = 4;
-  int cl = 1;                  // CTAs per work unit (1: every CTA owns its rows; PIX_CL: cluster plan)
+  int D = PIX_D;               // hidden width of the checkpoint (the grid-wide executor is built for 256 only)
+  bool has_v1 = false;         // stage table / blob of the grid-wide executor built (D == 256)
+  int cl = 1;                  // CTAs per work unit
   bool fused = false;          // 52-stage plan (EPI_HRESF / EPI_HGATE2 / EPI_OUT1F), else the plain 84-stage plan
   int sched = 1;               // 0 plain, 1 fused, 2 fused + vert_to_horiz moved into the horizontal pass (EPI_V2H1)
   PixLayout lay;
@@ -62,7 +62,7 @@ struct PixelPlan {
   float* d_arena = nullptr;
   unsigned* d_barrier = nullptr;
   Layer emb_aud, fuse_v_a, fuse_h_a;  // audio terms (precomputed per call for all rows)
-  void* p2 = nullptr;          // Plan2 of the cluster-per-8-samples kernel (pixelcnn2.inc)
+  void* p3 = nullptr;          // Plan3 of the cluster-resident executor (pixelcnn3.inc)
   unsigned long long* d_trace = nullptr;  // stage trace buffer (ts_pixelcnn_trace)
   int trace_row = -1;
   bool timing = false, pending = false;
@@ -76,6 +76,7 @@ void pixelcnn_generate_act(ts_engine* e, const Act3& aud, const int64_t* label, 
                            bool logits_all = false);
 // idx [B,T,2] -> idx_c [2][B][T]; optionally copies idx to codes_out
 void split_codes(ts_engine* e, const int64_t* idx, int64_t* idx_c, int B, int T, int64_t* codes_out, cudaStream_t s);
+void pixel_destroy(ts_engine* e);
 void face_destroy(ts_engine* e);
 void mfcc_destroy(ts_engine* e);
 
