@@ -10,7 +10,7 @@ torch.set_grad_enabled(False)
 row = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 ck = synth.body_pixel_checkpoint(0)
 e = Engine(0); e.load_pixelcnn(ck["generator"]); e.load_audioenc(ck["audioencoder"])
-B, T = 64, 75
+B, T = (int(sys.argv[2]) if len(sys.argv) > 2 else 64), 75
 mfcc = synth.synth_mfcc(B, 4 * T).cuda(); label = (torch.arange(B) % 4).cuda()
 noise = torch.empty(2 * T, B, 2048, device='cuda').exponential_(1)
 a = e.audio_encode(mfcc)

@@ -118,10 +118,10 @@ static std::vector<std::vector<Job>> build_stages(int L, int D = PIX_D) {
   return st;
 }
 
-static PixLayout make_layout(int L, int hvslots) {
+static PixLayout make_layout(int L, int hvslots, int MB = PIX_MB) {
   PixLayout a;
   int o = 0;
-  auto take = [&](int nseg) { int r = o; o += nseg * PIX_SEG; return r; };
+  auto take = [&](int nseg) { int r = o; o += nseg * PIX_D * MB; return r; };
   a.E = take(4 * 2);
   a.XV1P = take(2);
   a.XV = take(L * 2 * 2);
@@ -492,55 +492,56 @@ __device__ __forceinline__ bool task_active(const PixTask& t, int r, int log_r0)
 __device__ __forceinline__ uint32_t task_bytes(const PixTask& t) { return (uint32_t)((t.K + 1) * t.rpad) * 4u; }
 
 // arena offsets (floats) of the K segments of a matmul task; returns the segment count
-template <bool S2 = false>
+template <int MB, bool S2 = false>
 __device__ __forceinline__ int resolve_segments(const PixTask& t, int pass, int r, const PixLayout& a, int L, int* seg) {
+  constexpr int SEG = PIX_D * MB;
   if constexpr (S2) {   // schedule 2: one HV slot per layer, single-column vert_to_horiz
     if (t.epi == EPI_V2H || t.epi == EPI_V2H1) {
       const int col = t.epi == EPI_V2H1 ? t.col : pass;
-      seg[0] = a.HV + ((t.layer * 2 + col) * 2) * PIX_SEG;
-      seg[1] = seg[0] + PIX_SEG;
+      seg[0] = a.HV + ((t.layer * 2 + col) * 2) * SEG;
+      seg[1] = seg[0] + SEG;
       return 2;
     }
   }
   switch (t.epi) {
     case EPI_VERT0:
       for (int kh = 0; kh < 3; ++kh)
-        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.E + ((((r - 3 + kh) & 3) * 2) + ci) * PIX_SEG;
+        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.E + ((((r - 3 + kh) & 3) * 2) + ci) * SEG;
       return 6;
     case EPI_VERT:
       for (int kh = 0; kh < 2; ++kh)
-        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.XV + ((t.layer * 2 + ((r - 1 + kh) & 1)) * 2 + ci) * PIX_SEG;
+        for (int ci = 0; ci < 2; ++ci) seg[kh * 2 + ci] = a.XV + ((t.layer * 2 + ((r - 1 + kh) & 1)) * 2 + ci) * SEG;
       return 4;
     case EPI_V2H:
-      seg[0] = a.HV + (((t.layer & 1) * 2 + pass) * 2) * PIX_SEG;
-      seg[1] = seg[0] + PIX_SEG;
+      seg[0] = a.HV + (((t.layer & 1) * 2 + pass) * 2) * SEG;
+      seg[1] = seg[0] + SEG;
       return 2;
-    case EPI_FUSEV: seg[0] = a.XV1P + pass * PIX_SEG; return 1;
+    case EPI_FUSEV: seg[0] = a.XV1P + pass * SEG; return 1;
     case EPI_HGATE:
       if (t.layer == 0) {
         if (t.col == 0) return 0;
-        seg[0] = a.E + ((r & 3) * 2 + 0) * PIX_SEG;
+        seg[0] = a.E + ((r & 3) * 2 + 0) * SEG;
         return 1;
       }
-      seg[0] = a.XH + (0 * (L + 1) + t.layer) * PIX_SEG;
+      seg[0] = a.XH + (0 * (L + 1) + t.layer) * SEG;
       if (t.col == 0) return 1;
-      seg[1] = a.XH + (1 * (L + 1) + t.layer) * PIX_SEG;
+      seg[1] = a.XH + (1 * (L + 1) + t.layer) * SEG;
       return 2;
-    case EPI_HRES: seg[0] = a.G + (t.layer & 1) * PIX_SEG; return 1;
+    case EPI_HRES: seg[0] = a.G + (t.layer & 1) * SEG; return 1;
     case EPI_HRESF: seg[0] = a.G; return 1;
     case EPI_HGATE2:
-      seg[0] = a.G + ((t.layer - 1) & 1) * PIX_SEG;
-      seg[1] = a.XH + (t.col * (L + 1) + t.layer - 1) * PIX_SEG;
+      seg[0] = a.G + ((t.layer - 1) & 1) * SEG;
+      seg[1] = a.XH + (t.col * (L + 1) + t.layer - 1) * SEG;
       if (t.col == 0) return 2;
-      seg[2] = a.XH + (0 * (L + 1) + t.layer) * PIX_SEG;
+      seg[2] = a.XH + (0 * (L + 1) + t.layer) * SEG;
       return 3;
     case EPI_OUT1F:
-      seg[0] = a.G + ((L - 1) & 1) * PIX_SEG;
-      seg[1] = a.XH + (t.col * (L + 1) + L - 1) * PIX_SEG;
+      seg[0] = a.G + ((L - 1) & 1) * SEG;
+      seg[1] = a.XH + (t.col * (L + 1) + L - 1) * SEG;
       return 2;
     case EPI_FUSEH: seg[0] = a.XHP; return 1;
-    case EPI_OUT1: seg[0] = a.XH + (t.col * (L + 1) + L) * PIX_SEG; return 1;
-    case EPI_OUT2: seg[0] = a.Y; seg[1] = a.Y + PIX_SEG; return 2;
+    case EPI_OUT1: seg[0] = a.XH + (t.col * (L + 1) + L) * SEG; return 1;
+    case EPI_OUT2: seg[0] = a.Y; seg[1] = a.Y + SEG; return 2;
   }
   return 0;
 }
@@ -549,6 +550,7 @@ __device__ __forceinline__ int resolve_segments(const PixTask& t, int pass, int 
 template <int RC>
 __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
                                         float* red, int warp, int lane) {
+  constexpr int MB = 64;   // lane owns samples 2*lane, 2*lane+1
   float2 acc[4 * RC];
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -559,10 +561,10 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
   const int kbeg = slice * kper;
   constexpr int U = 32;   // K = 256 stages issue their whole K slice in one batch of loads
   for (int k0 = kbeg; k0 < kbeg + kper; k0 += U) {
-    const float* base = arena + seg[k0 >> 8] + ((k0 & 255) << 6) + lane * 2;
+    const float* base = arena + seg[k0 >> 8] + ((k0 & 255) * MB) + lane * 2;
     float2 x[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) x[u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+    for (int u = 0; u < U; ++u) x[u] = __ldcg(reinterpret_cast<const float2*>(base + u * MB));
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float4* w4 = reinterpret_cast<const float4*>(Wsm + (size_t)(k0 + u) * (4 * RC));
@@ -578,7 +580,7 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
   }
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j)
-    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * MB + lane * 2]) = acc[j];
 }
 
 // Same partial products (same per-accumulator summation order -> bit-identical), software-pipelined: the
@@ -588,6 +590,7 @@ __device__ __forceinline__ void mm_rows(const float* __restrict__ Wsm, int K, co
 template <int RC, int G>
 __device__ __forceinline__ void mm_rows_pipe(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
                                              float* red, int warp, int lane) {
+  constexpr int MB = 64;
   float2 acc[4 * RC];
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -599,9 +602,9 @@ __device__ __forceinline__ void mm_rows_pipe(const float* __restrict__ Wsm, int 
 #pragma unroll
   for (int g = 0; g < G; ++g) {   // kper is a multiple of G * GS = 32
     const int k = kbeg + g * GS;
-    const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+    const float* base = arena + seg[k >> 8] + ((k & 255) * MB) + lane * 2;
 #pragma unroll
-    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * MB));
   }
   for (int k0 = kbeg; k0 < kend; k0 += G * GS) {
     const bool more = k0 + G * GS < kend;
@@ -622,15 +625,15 @@ __device__ __forceinline__ void mm_rows_pipe(const float* __restrict__ Wsm, int 
       }
       if (more) {
         const int k = k0 + G * GS + g * GS;
-        const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+        const float* base = arena + seg[k >> 8] + ((k & 255) * MB) + lane * 2;
 #pragma unroll
-        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * PIX_MB));
+        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const float2*>(base + u * MB));
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j)
-    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+    *reinterpret_cast<float2*>(&red[(slice * PIX_MAXROWS + j) * MB + lane * 2]) = acc[j];
 }
 
 // Blackwell packed fp32 FMA (SASS FFMA2): two IEEE fp32 FMAs per lane per instruction — the same results as
@@ -645,6 +648,7 @@ __device__ __forceinline__ void fma2(unsigned long long& acc, float w, unsigned 
 template <int RC, int G>
 __device__ __forceinline__ void mm_rows_pipe2(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
                                               float* red, int warp, int lane) {
+  constexpr int MB = 64;
   unsigned long long acc[4 * RC];
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j) acc[j] = 0ull;
@@ -656,9 +660,9 @@ __device__ __forceinline__ void mm_rows_pipe2(const float* __restrict__ Wsm, int
 #pragma unroll
   for (int g = 0; g < G; ++g) {   // kper is a multiple of G * GS = 32
     const int k = kbeg + g * GS;
-    const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+    const float* base = arena + seg[k >> 8] + ((k & 255) * MB) + lane * 2;
 #pragma unroll
-    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * PIX_MB));
+    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * MB));
   }
   for (int k0 = kbeg; k0 < kend; k0 += G * GS) {
     const bool more = k0 + G * GS < kend;
@@ -679,21 +683,105 @@ __device__ __forceinline__ void mm_rows_pipe2(const float* __restrict__ Wsm, int
       }
       if (more) {
         const int k = k0 + G * GS + g * GS;
-        const float* base = arena + seg[k >> 8] + ((k & 255) << 6) + lane * 2;
+        const float* base = arena + seg[k >> 8] + ((k & 255) * MB) + lane * 2;
 #pragma unroll
-        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * PIX_MB));
+        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(reinterpret_cast<const unsigned long long*>(base + u * MB));
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 4 * RC; ++j)
-    *reinterpret_cast<unsigned long long*>(&red[(slice * PIX_MAXROWS + j) * PIX_MB + lane * 2]) = acc[j];
+    *reinterpret_cast<unsigned long long*>(&red[(slice * PIX_MAXROWS + j) * MB + lane * 2]) = acc[j];
 }
 
-__device__ __forceinline__ float red_sum(const float* red, int j, int m) {
-  float s = red[(0 * PIX_MAXROWS + j) * PIX_MB + m];
+__device__ __forceinline__ void fma2p(unsigned long long& acc, unsigned long long wp, float x) {
+  unsigned long long xx;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(xx) : "f"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(wp), "l"(xx));
+}
+
+// arena index of (channel, sample) inside a tensor: [channel][MB samples] (channels beyond 256 continue into the next segment)
+template <int MB>
+__device__ __forceinline__ int ax(int ch, int m) { return ch * MB + m; }
+
+// Batch tiles below 64 samples (MB = 8 / 16 / 32): lane = (sample m, row group rq) with 32 / MB row groups, each lane
+// owns RPL = rpad * MB / 32 consecutive weight rows of the task for ONE sample.  Same K slicing (8 contiguous slices, one
+// per warp, summed in k order) and the same slice-ordered reduction as the 64-sample kernels, so every output is
+// bit-identical whatever tile a sample runs in.  Packed fp32 FMAs over ROW pairs when RPL is even.
+template <int RC, int MB>
+__device__ __forceinline__ void mm_rows_small(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
+                                              float* red, int warp, int lane) {
+  constexpr int RPL = RC * MB / 8, RPAD = 4 * RC;
+  constexpr bool PACK = (RPL % 2) == 0;
+  const int m = lane % MB, rq = lane / MB;
+  float acc[PACK ? 1 : RPL];
+  unsigned long long acc2[PACK ? RPL / 2 : 1];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) s += red[(w * PIX_MAXROWS + j) * PIX_MB + m];
+  for (int j = 0; j < (PACK ? 1 : RPL); ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < (PACK ? RPL / 2 : 1); ++j) acc2[j] = 0ull;
+  const int kper = K >> 3;  // multiple of 32
+  const int slice = (warp + blockIdx.x) & 7;
+  const int kbeg = slice * kper, kend = kbeg + kper;
+  constexpr int G = 4, GS = 8;   // ring of 4 groups x 8 activation loads, re-issued as soon as a group's FMAs are done
+  float x[G][GS];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int k = kbeg + g * GS;
+    const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
+#pragma unroll
+    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
+  }
+  const float* wl = Wsm + rq * RPL;
+  for (int k0 = kbeg; k0 < kend; k0 += G * GS) {
+    const bool more = k0 + G * GS < kend;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int u = 0; u < GS; ++u) {
+        const float* wr = wl + (size_t)(k0 + g * GS + u) * RPAD;
+        const float xv = x[g][u];
+        if constexpr (RPL % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < RPL / 4; ++q) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wr + 4 * q);
+            fma2p(acc2[2 * q], w.x, xv);
+            fma2p(acc2[2 * q + 1], w.y, xv);
+          }
+        } else if constexpr (PACK) {
+#pragma unroll
+          for (int q = 0; q < RPL / 2; ++q) fma2p(acc2[q], *reinterpret_cast<const unsigned long long*>(wr + 2 * q), xv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < RPL; ++j) acc[j] = fmaf(wr[j], xv, acc[j]);
+        }
+      }
+      if (more) {
+        const int k = k0 + G * GS + g * GS;
+        const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < RPL; ++j) {
+    float v;
+    if constexpr (PACK) {
+      const unsigned long long a2 = acc2[j >> 1];
+      v = __uint_as_float((j & 1) ? (unsigned)(a2 >> 32) : (unsigned)(a2 & 0xffffffffu));
+    } else {
+      v = acc[j];
+    }
+    red[(slice * PIX_MAXROWS + rq * RPL + j) * MB + m] = v;
+  }
+}
+
+template <int MB>
+__device__ __forceinline__ float red_sum(const float* red, int j, int m) {
+  float s = red[(0 * PIX_MAXROWS + j) * MB + m];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red[(w * PIX_MAXROWS + j) * MB + m];
   return s;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -705,30 +793,31 @@ struct EpiPre {  // epilogue operands fetched before the grid-barrier wait (they
 };
 
 // operands of thread-item `tid` of an H-pass task whose epilogue has at most one item per thread
-template <bool S2 = false>
+template <int MB, bool S2 = false>
 __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixArgs& A, int r) {
+  constexpr int SEG = PIX_D * MB;
   EpiPre p;
   p.a = 0.f; p.b = 0.f; p.valid = false;
   if constexpr (S2) {   // schedule 2: the vert_to_horiz operand of a gate is written by the PREVIOUS stage
     if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) return p;
   }
-  const int tid = threadIdx.x, m = tid & (PIX_MB - 1), j = tid >> 6;
+  const int tid = threadIdx.x, m = tid & (MB - 1), j = tid / MB;
   const PixLayout& a = A.lay;
   if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
-    if (j < (t.nrows >> 1) && (t.nrows >> 1) * PIX_MB <= PIX_THREADS) {
+    if (j < (t.nrows >> 1) && (t.nrows >> 1) * MB <= PIX_THREADS) {
       const int q = (t.row0 >> 1) + j;
-      const float* v2h = A.arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
-      p.a = __ldcg(v2h + q * PIX_MB + m);
-      p.b = __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
+      const float* v2h = A.arena + a.V2H + ((t.layer * 2 + t.col) * 2) * SEG;
+      p.a = __ldcg(v2h + ax<MB>(q, m));
+      p.b = __ldcg(v2h + ax<MB>(PIX_D + q, m));
       p.valid = true;
     }
   } else if (t.epi == EPI_HRES && t.layer > 0 && !A.fused) {   // fused plan: x_h[l] is written by the previous stage
-    if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
-      p.a = __ldcg(A.arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + (t.row0 + j) * PIX_MB + m);
+    if (j < t.nrows && t.nrows * MB <= PIX_THREADS) {
+      p.a = __ldcg(A.arena + a.XH + (t.col * (A.L + 1) + t.layer) * SEG + ax<MB>(t.row0 + j, m));
       p.valid = true;
     }
   } else if (t.epi == EPI_FUSEH || t.epi == EPI_HRESF) {
-    if (j < t.nrows && t.nrows * PIX_MB <= PIX_THREADS) {
+    if (j < t.nrows && t.nrows * MB <= PIX_THREADS) {
       p.a = m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + t.row0 + j] : 0.f;
       p.valid = true;
     }
@@ -736,8 +825,9 @@ __device__ __forceinline__ EpiPre prefetch_epilogue(const PixTask& t, const PixA
   return p;
 }
 
-template <int PIPE, bool S2 = false>
+template <int PIPE, int MB, bool S2 = false>
 __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const float* Wsm, float* red, const EpiPre& pre) {
+  constexpr int SEG = PIX_D * MB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PixLayout& a = A.lay;
   const int npass = (t.epi == EPI_V2H || t.epi == EPI_FUSEV) ? 2 : 1;
@@ -745,10 +835,17 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
   float* arena = A.arena;
   for (int pass = 0; pass < npass; ++pass) {
     int s_seg[6];  // at most 6 segments (EPI_VERT0)
-    resolve_segments<S2>(t, pass, r, a, A.L, s_seg);
+    resolve_segments<MB, S2>(t, pass, r, a, A.L, s_seg);
     if (pass > 0) __syncthreads();  // previous pass's epilogue finished reading red
     if (t.K > 0) {
-      if constexpr (PIPE == 5) {
+      if constexpr (MB < 64) {   // small batch tiles: lane = (sample, row group), FFMA2 over row pairs
+        switch (t.rpad >> 2) {
+          case 1: mm_rows_small<1, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 2: mm_rows_small<2, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          case 3: mm_rows_small<3, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          default: mm_rows_small<4, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        }
+      } else if constexpr (PIPE == 5) {
         switch (t.rpad >> 2) {
           case 1: mm_rows_pipe2<1, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
           case 2: mm_rows_pipe2<2, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
@@ -773,56 +870,56 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
     }
     __syncthreads();
     const bool pairs = (t.epi == EPI_VERT0 || t.epi == EPI_VERT || t.epi == EPI_HGATE || t.epi == EPI_HGATE2);
-    const int items = (pairs ? t.nrows >> 1 : t.nrows) * PIX_MB;
+    const int items = (pairs ? t.nrows >> 1 : t.nrows) * MB;
     for (int it = tid; it < items; it += PIX_THREADS) {
-      const int m = it & (PIX_MB - 1), j = it >> 6;
+      const int m = it & (MB - 1), j = it / MB;
       if (pairs) {
         const int q = (t.row0 >> 1) + j;  // gate channel
-        float at = (t.K > 0 ? red_sum(red, 2 * j, m) : 0.f) + bias[2 * j];
-        float as = (t.K > 0 ? red_sum(red, 2 * j + 1, m) : 0.f) + bias[2 * j + 1];
-        const float* cls = arena + a.CLS + (t.layer * 2) * PIX_SEG;
-        float ct = cls[q * PIX_MB + m], cs = cls[(PIX_D + q) * PIX_MB + m];
+        float at = (t.K > 0 ? red_sum<MB>(red, 2 * j, m) : 0.f) + bias[2 * j];
+        float as = (t.K > 0 ? red_sum<MB>(red, 2 * j + 1, m) : 0.f) + bias[2 * j + 1];
+        const float* cls = arena + a.CLS + (t.layer * 2) * SEG;
+        float ct = cls[ax<MB>(q, m)], cs = cls[ax<MB>(PIX_D + q, m)];
         if (t.epi == EPI_HGATE || t.epi == EPI_HGATE2) {
-          const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG;
-          float vt = pre.valid ? pre.a : __ldcg(v2h + q * PIX_MB + m);
-          float vs = pre.valid ? pre.b : __ldcg(v2h + (PIX_D + q) * PIX_MB + m);
+          const float* v2h = arena + a.V2H + ((t.layer * 2 + t.col) * 2) * SEG;
+          float vt = pre.valid ? pre.a : __ldcg(v2h + ax<MB>(q, m));
+          float vs = pre.valid ? pre.b : __ldcg(v2h + ax<MB>(PIX_D + q, m));
           float zt = (vt + at) + ct;
           float zs = (vs + as) + cs;
-          arena[a.G + (t.layer & 1) * PIX_SEG + q * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+          arena[a.G + (t.layer & 1) * SEG + ax<MB>(q, m)] = tanhf(zt) * sigmoidf_(zs);
         } else {
-          float* hv = arena + a.HV + (((S2 ? t.layer : (t.layer & 1)) * 2 + t.col) * 2) * PIX_SEG;
-          hv[q * PIX_MB + m] = at;
-          hv[(PIX_D + q) * PIX_MB + m] = as;
+          float* hv = arena + a.HV + (((S2 ? t.layer : (t.layer & 1)) * 2 + t.col) * 2) * SEG;
+          hv[ax<MB>(q, m)] = at;
+          hv[ax<MB>(PIX_D + q, m)] = as;
           float g = tanhf(at + ct) * sigmoidf_(as + cs);
-          if (t.epi == EPI_VERT0) arena[a.XV1P + t.col * PIX_SEG + q * PIX_MB + m] = g;
+          if (t.epi == EPI_VERT0) arena[a.XV1P + t.col * SEG + ax<MB>(q, m)] = g;
           else if (t.layer + 1 < A.L)
-            arena[a.XV + (((t.layer + 1) * 2 + (r & 1)) * 2 + t.col) * PIX_SEG + q * PIX_MB + m] = g;
+            arena[a.XV + (((t.layer + 1) * 2 + (r & 1)) * 2 + t.col) * SEG + ax<MB>(q, m)] = g;
         }
       } else {
         const int ch = t.row0 + j;
-        float v = red_sum(red, j, m) + bias[j];
+        float v = red_sum<MB>(red, j, m) + bias[j];
         switch (t.epi) {
-          case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * PIX_SEG + ch * PIX_MB + m] = v; break;
+          case EPI_V2H: arena[a.V2H + ((t.layer * 2 + pass) * 2) * SEG + ax<MB>(ch, m)] = v; break;
           case EPI_V2H1:
-            if constexpr (S2) arena[a.V2H + ((t.layer * 2 + t.col) * 2) * PIX_SEG + ch * PIX_MB + m] = v;
+            if constexpr (S2) arena[a.V2H + ((t.layer * 2 + t.col) * 2) * SEG + ax<MB>(ch, m)] = v;
             break;
           case EPI_FUSEV: {
             float au = m < A.B ? A.audv[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f;
-            arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * PIX_SEG + ch * PIX_MB + m] = v + au;
+            arena[a.XV + ((1 * 2 + (r & 1)) * 2 + pass) * SEG + ax<MB>(ch, m)] = v + au;
           } break;
           case EPI_HRES:
-            if (t.layer == 0) arena[a.XHP + ch * PIX_MB + m] = v;
+            if (t.layer == 0) arena[a.XHP + ax<MB>(ch, m)] = v;
             else {
-              float xh = pre.valid ? pre.a : __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * PIX_SEG + ch * PIX_MB + m);
-              arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * PIX_SEG + ch * PIX_MB + m] = v + xh;
+              float xh = pre.valid ? pre.a : __ldcg(arena + a.XH + (t.col * (A.L + 1) + t.layer) * SEG + ax<MB>(ch, m));
+              arena[a.XH + (t.col * (A.L + 1) + t.layer + 1) * SEG + ax<MB>(ch, m)] = v + xh;
             }
             break;
           case EPI_FUSEH: case EPI_HRESF: {
             float au = pre.valid ? pre.a : (m < A.B ? A.audh[((size_t)m * A.Ttot + r) * PIX_D + ch] : 0.f);
-            arena[a.XH + (t.col * (A.L + 1) + 1) * PIX_SEG + ch * PIX_MB + m] = v + au;
+            arena[a.XH + (t.col * (A.L + 1) + 1) * SEG + ax<MB>(ch, m)] = v + au;
           } break;
-          case EPI_OUT1: case EPI_OUT1F: arena[a.Y + ch * PIX_MB + m] = v > 0.f ? v : 0.f; break;
-          case EPI_OUT2: arena[a.LOG + ch * PIX_MB + m] = v; break;
+          case EPI_OUT1: case EPI_OUT1F: arena[a.Y + ax<MB>(ch, m)] = v > 0.f ? v : 0.f; break;
+          case EPI_OUT2: arena[a.LOG + ax<MB>(ch, m)] = v; break;
         }
       }
     }
@@ -833,8 +930,9 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
 // then embedding gather of the sampled code into the E ring.  One CTA per sample.
 // QPRE (schedule 2 only): the sampler noise of this position was loaded before the grid-barrier wait (it is an
 // input of the call, independent of every stage) and arrives in qpre[8].
-template <bool QPRE = false>
+template <int MB, bool QPRE = false>
 __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m, float* red, const float* qpre = nullptr) {
+  constexpr int SEG = PIX_D * MB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c = t.col;
   float* sf = red;                                  // [8] scratch
@@ -845,7 +943,7 @@ __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m
   float l[8];
   if (have_logits) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) l[j] = __ldcg(A.arena + A.lay.LOG + (tid + 256 * j) * PIX_MB + m);
+    for (int j = 0; j < 8; ++j) l[j] = __ldcg(A.arena + A.lay.LOG + ax<MB>(tid + 256 * j, m));
     if (A.logits_out) {
       float* dst = A.logits_out + ((size_t)(2 * (r - A.log_r0) + c) * A.B + m) * PIX_NCODE;
 #pragma unroll
@@ -902,20 +1000,20 @@ __device__ void run_sample_task(const PixTask& t, const PixArgs& A, int r, int m
   }
   if (r >= A.T0 && tid == 0) A.idx_out[((size_t)m * (A.Ttot - A.T0) + (r - A.T0)) * 2 + c] = code;
   // embedding gather into the ring slot of this row (x_v = x_h = embedding(code) at layer 0)
-  A.arena[A.lay.E + ((r & 3) * 2 + c) * PIX_SEG + tid * PIX_MB + m] = A.emb[(size_t)code * PIX_D + tid];
+  A.arena[A.lay.E + ((r & 3) * 2 + c) * SEG + ax<MB>(tid, m)] = A.emb[(size_t)code * PIX_D + tid];
   if (t.K) {
     // fused plan: layer-0 gate of column 1 (its matmul input is embedding[code] only -> gathered from T0)
     const float2 tw = *reinterpret_cast<const float2*>(A.blob + t.wofs + (size_t)code * (2 * PIX_D) + 2 * tid);
-    const float* v2h = A.arena + A.lay.V2H + ((0 * 2 + 1) * 2) * PIX_SEG;
+    const float* v2h = A.arena + A.lay.V2H + ((0 * 2 + 1) * 2) * SEG;
     const float* cls = A.arena + A.lay.CLS;
-    const float zt = (__ldcg(v2h + tid * PIX_MB + m) + tw.x) + cls[tid * PIX_MB + m];
-    const float zs = (__ldcg(v2h + (PIX_D + tid) * PIX_MB + m) + tw.y) + cls[(PIX_D + tid) * PIX_MB + m];
-    A.arena[A.lay.G + tid * PIX_MB + m] = tanhf(zt) * sigmoidf_(zs);
+    const float zt = (__ldcg(v2h + ax<MB>(tid, m)) + tw.x) + cls[ax<MB>(tid, m)];
+    const float zs = (__ldcg(v2h + ax<MB>(PIX_D + tid, m)) + tw.y) + cls[ax<MB>(PIX_D + tid, m)];
+    A.arena[A.lay.G + ax<MB>(tid, m)] = tanhf(zt) * sigmoidf_(zs);
   }
 }
 
 constexpr int PIX_MAXSTAGES = 160;  // this CTA's column of the stage table is kept in shared memory
-constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * PIX_MB) * sizeof(float) + 64 + PIX_MAXSTAGES * sizeof(PixTask);
+constexpr size_t PIX_SMEM = (size_t)(2 * PIX_WBUF + 8 * PIX_MAXROWS * 64) * sizeof(float) + 64 + PIX_MAXSTAGES * sizeof(PixTask);
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -926,12 +1024,12 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // TRACE: a second instantiation of the persistent kernel that stamps, for one latent row, when each CTA's thread 0
 // has its weights, leaves the grid barrier, finishes its task and has arrived again (ts_pixelcnn_trace): the
 // measurement the stage cost model and the CTA split should be fitted to.  The default kernel is TRACE = false.
-template <bool PERSISTENT, int PIPE, bool TRACE = false, bool S2 = false>
+template <bool PERSISTENT, int PIPE, bool TRACE = false, bool S2 = false, int MB = 64>
 __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int r_single, int s_single) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* wbuf = reinterpret_cast<float*>(smem_raw);
   float* red = wbuf + 2 * PIX_WBUF;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * PIX_MAXROWS * PIX_MB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 8 * PIX_MAXROWS * 64);
   PixTask* tasks = reinterpret_cast<PixTask*>(bars + 8);
   const int tid = threadIdx.x, cta = blockIdx.x;
 
@@ -939,12 +1037,12 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     // debug cross-check mode: one launch per stage, weights copied synchronously
     const PixTask t = A.table[(size_t)s_single * A.ncta + cta];
     if (!task_active(t, r_single, A.log_r0)) return;
-    if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task(t, A, r_single, cta, red); return; }
+    if (t.epi == EPI_SAMPLE) { if (cta < A.B) run_sample_task<MB>(t, A, r_single, cta, red); return; }
     const int nf = (t.K + 1) * t.rpad;
     for (int i = tid; i < nf; i += PIX_THREADS) wbuf[i] = A.blob[t.wofs + i];
     __syncthreads();
     EpiPre pre; pre.a = pre.b = 0.f; pre.valid = false;
-    run_matmul_task<0, S2>(t, A, r_single, wbuf, red, pre);
+    run_matmul_task<0, MB, S2>(t, A, r_single, wbuf, red, pre);
     return;
   }
 
@@ -986,7 +1084,7 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     const bool has_w = active && t.epi != EPI_SAMPLE;  // K == 0 tasks still stage their bias row
     EpiPre pre;
     pre.a = pre.b = 0.f; pre.valid = false;
-    if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue<S2>(t, A, r);   // in flight while we wait below
+    if (active && t.epi != EPI_SAMPLE) pre = prefetch_epilogue<MB, S2>(t, A, r);   // in flight while we wait below
     float qpre[8];
     if constexpr (S2) {
       if (active && t.epi == EPI_SAMPLE && cta < A.B && r >= A.T0) {
@@ -1004,10 +1102,10 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
     if constexpr (TRACE) { if (tr) tr[1] = globaltimer_ns(); }
     if (active) {
       if (t.epi == EPI_SAMPLE) {
-        if constexpr (S2) { if (cta < A.B) run_sample_task<true>(t, A, r, cta, red, qpre); }
-        else { if (cta < A.B) run_sample_task(t, A, r, cta, red); }
+        if constexpr (S2) { if (cta < A.B) run_sample_task<MB, true>(t, A, r, cta, red, qpre); }
+        else { if (cta < A.B) run_sample_task<MB>(t, A, r, cta, red); }
       }
-      else run_matmul_task<PIPE, S2>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
+      else run_matmul_task<PIPE, MB, S2>(t, A, r, wbuf + buf * PIX_WBUF, red, pre);
     }
     if constexpr (TRACE) { __syncthreads(); if (tr) tr[2] = globaltimer_ns(); }
     grid_arrive(A.barrier);
@@ -1019,11 +1117,11 @@ __global__ void __launch_bounds__(PIX_THREADS, 1) pixelcnn_kernel(PixArgs A, int
 #include "pixelcnn3.inc"
 
 __global__ void build_cls_kernel(const float* __restrict__ cls_w, const int64_t* __restrict__ label, float* arena, int cls_off,
-                                 int L, int ncls, int B) {
+                                 int L, int ncls, int B, int MB) {
   // CLS[l][ch][m] = class_cond_embedding_l[label[m]][ch]
-  int n = L * 2 * PIX_D * PIX_MB;
+  int n = L * 2 * PIX_D * MB;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int m = i & (PIX_MB - 1), ch = (i >> 6) % (2 * PIX_D), l = i / (2 * PIX_D * PIX_MB);
+    int m = i % MB, ch = (i / MB) % (2 * PIX_D), l = i / (2 * PIX_D * MB);
     float v = 0.f;
     if (m < B) {
       long long lb = label[m];
@@ -1095,16 +1193,26 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   }
   if (B > PIX_MB)
     fail(TS_ERR_UNSUPPORTED, "pixelcnn: the grid-wide executor takes %d samples per call (got %d); the host shim chunks larger batches", PIX_MB, B);
-  TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)P->lay.total * sizeof(float), s));
+  // batch tile of the launch: the smallest of 8 / 16 / 32 / 64 samples that holds the batch (TS_PIX_TILE overrides);
+  // every output is bit-identical whatever tile a sample runs in (same K slicing and reduction order)
+  int MB = B <= 16 ? 16 : B <= 32 ? 32 : 64;    // the 8-sample tile measures slower than the 16-sample one (B200)
+  if (const char* v = getenv("TS_PIX_TILE")) {
+    const int t = atoi(v);
+    if ((t == 8 || t == 16 || t == 32 || t == 64) && t >= B) MB = t;
+  }
+  const bool tracing = P->d_trace && P->trace_row >= 0;
+  if (P->sched == 2 || (tracing && MB != 16)) MB = 64;   // schedule 2 / the stage trace: 64-sample tile (trace also 16)
+  const PixLayout lay = make_layout(P->L, P->sched == 2 ? P->L : 2, MB);
+  TS_CUDA(cudaMemsetAsync(P->d_arena, 0, (size_t)lay.total * sizeof(float), s));
   TS_CUDA(cudaMemsetAsync(P->d_barrier, 0, 4096, s));
-  build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, P->lay.CLS, P->L, P->nclasses, B);
+  build_cls_kernel<<<148, 256, 0, s>>>(P->d_cls, label, P->d_arena, lay.CLS, P->L, P->nclasses, B, MB);
   e->launches++;
   TS_CUDA(cudaGetLastError());
 
   PixArgs A;
   A.table = P->d_table; A.blob = P->d_blob; A.arena = P->d_arena; A.emb = P->d_emb;
   A.audv = audv; A.audh = audh; A.noise = noise; A.pre = pre; A.idx_out = idx_out; A.logits_out = logits_out;
-  A.barrier = P->d_barrier; A.lay = P->lay;
+  A.barrier = P->d_barrier; A.lay = lay;
   A.B = B; A.T0 = T0; A.Ttot = Ttot; A.log_r0 = logits_all ? 0 : T0; A.L = P->L; A.nstages = P->nstages; A.ncta = P->ncta;
   A.fused = P->fused ? 1 : 0;
   A.trace = P->d_trace; A.trace_row = P->trace_row;
@@ -1112,8 +1220,11 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     // A/B switch: 0 = burst loads + scalar FFMA, 4 = pipelined loads + scalar FFMA, 5 (default) = pipelined loads + FFMA2
     static const int pipe = getenv("TS_PIX_PIPE") ? atoi(getenv("TS_PIX_PIPE")) : 5;
     void* fn = pipe == 0 ? (void*)pixelcnn_kernel<true, 0> : pipe == 4 ? (void*)pixelcnn_kernel<true, 4> : (void*)pixelcnn_kernel<true, 5>;
-    if (P->d_trace && P->trace_row >= 0) fn = (void*)pixelcnn_kernel<true, 5, true>;
-    if (P->sched == 2) fn = (P->d_trace && P->trace_row >= 0) ? (void*)pixelcnn_kernel<true, 5, true, true> : (void*)pixelcnn_kernel<true, 5, false, true>;
+    if (MB == 32) fn = (void*)pixelcnn_kernel<true, 5, false, false, 32>;
+    if (MB == 16) fn = (void*)pixelcnn_kernel<true, 5, false, false, 16>;
+    if (MB == 8) fn = (void*)pixelcnn_kernel<true, 5, false, false, 8>;
+    if (tracing) fn = MB == 16 ? (void*)pixelcnn_kernel<true, 5, true, false, 16> : (void*)pixelcnn_kernel<true, 5, true>;
+    if (P->sched == 2) fn = tracing ? (void*)pixelcnn_kernel<true, 5, true, true> : (void*)pixelcnn_kernel<true, 5, false, true>;
     TS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
@@ -1122,7 +1233,10 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
     e->launches++;
   } else {
-    auto fn1 = P->sched == 2 ? pixelcnn_kernel<false, 0, false, true> : pixelcnn_kernel<false, 0>;
+    void (*fn1)(PixArgs, int, int) = P->sched == 2 ? pixelcnn_kernel<false, 0, false, true> : pixelcnn_kernel<false, 0>;
+    if (MB == 32) fn1 = pixelcnn_kernel<false, 0, false, false, 32>;
+    if (MB == 16) fn1 = pixelcnn_kernel<false, 0, false, false, 16>;
+    if (MB == 8) fn1 = pixelcnn_kernel<false, 0, false, false, 8>;
     TS_CUDA(cudaFuncSetAttribute(fn1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIX_SMEM));
     for (int r = 0; r < Ttot; ++r)
       for (int st = 0; st < P->nstages; ++st) {
