@@ -84,7 +84,7 @@ int ts_pixelcnn_logits(ts_engine* e, const float* aud, const int64_t* label, con
                        float* logits_out, int B, int T, void* stream);
 
 /* VQVAE.decode(latents=...), nets/spg/vqvae_1d.py:201-208: idx [B,T] int64 -> out [B,C,4T]
- * (C = 39 body / 90 hand). */
+ * (C = ts_vq_dim(which): 39 body / 90 hand, 78 / 180 for 6-D). */
 int ts_vq_decode(ts_engine* e, int which, const int64_t* idx, float* out, int B, int T, void* stream);
 /* VQVAE.encode, :196-199: poses [B,F,C] -> idx [B,T] int64 (T=F/4), e_out (may be NULL) [B,64,T]. */
 int ts_vq_encode(ts_engine* e, int which, const float* poses, int64_t* idx, float* e_out, int B, int F,
@@ -95,8 +95,13 @@ int ts_vq_encode(ts_engine* e, int which, const float* poses, int64_t* idx, floa
 int ts_face_forward(ts_engine* e, const float* wave, const float* id, float* out, int B, int N, int frame,
                     void* stream);
 
+/* pose channels of the loaded VQ-VAE `which` (in_dim of nets/smplx_body_pixel.py:54-57: 39 / 90 axis-angle,
+ * 78 / 180 with convert_to_6d); 0 when not loaded. */
+int ts_vq_dim(ts_engine* e, int which);
+
 /* s2g_body_pixel.infer_on_audio core, nets/smplx_body_pixel.py:270-285, fused:
- * mfcc [B,64,M] -> codes [B,T,2] (may be NULL), poses [B,4T,129] (body 39 + hand 90). */
+ * mfcc [B,64,M] -> codes [B,T,2] (may be NULL), poses [B,4T,C] with C = ts_vq_dim(0) + ts_vq_dim(1)
+ * (body 39 + hand 90 = 129; 258 for the 6-D configs). */
 int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise, int64_t* codes,
                      float* poses, int B, int M, void* stream);
 
@@ -114,6 +119,20 @@ int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* 
 /* scripts/demo.py:185-188,216-219 (convert_to_6d configs): matrix_to_axis_angle(rotation_6d_to_matrix(x)),
  * data_utils/rotation_conversion.py:512-533,433-447.  d6 [n,6] -> aa [n,3] (device pointers). */
 int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, int64_t n, void* stream);
+
+/* ---- batched SMPL-X evaluation ---------------------------------------------------
+ * Replaces the per-frame smplx_model(...) calls of scripts/demo.py:122-152 (get_vertices) and data_utils/get_j.py:20-51
+ * (get_joints): smplx 0.1.28 SMPLX.forward + lbs (use_pca=False, flat_hand_mean=False, 300 betas, 100 expression
+ * coefficients, static face landmarks) for F frames per call, fp32.  Model tensors (host, fp32 / int64), named as in
+ * oracle/smplx_oracle.py: v_template [V,3], shapedirs [V,3,400], posedirs [486,3V], J_regressor [55,V], lbs_weights [V,55],
+ * pose_mean [165], parents [55], faces [Fc,3], lmk_faces_idx [L], lmk_bary_coords [L,3], extra_joint_idx [E]. */
+int ts_load_smplx(ts_engine* e, const ts_tensor* tensors, int n);
+int ts_smplx_dims(ts_engine* e, int* V, int* njoints);
+/* poses [F,265] in the reference's argument layout (jaw | leye | reye | global | body | lhand | rhand | expression,
+ * demo.py:129-138), betas [300] or NULL (zeros, demo.py:159) -> vertices [F,V,3] (may be NULL), joints
+ * [F,55+E+L,3] (may be NULL); use_expression = 0 evaluates with zero expression (get_vertices(exp=False)). */
+int ts_smplx_forward(ts_engine* e, const float* poses, const float* betas, int use_expression, float* vertices,
+                     float* joints, int F, void* stream);
 
 /* ---- introspection (tests / bench) ---------------------------------------------------------- */
 /* number of kernel launches issued by this engine since creation */
@@ -139,10 +158,11 @@ int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const 
  * 4: tcgen05 3xTF32 kernel, single CTA 128x256 tile; 2: same in clusters with TMA multicast of the operand boxes;
  * 0: everything on the fp32 FFMA kernel. */
 int ts_set_tensor_cores(ts_engine* e, int enable);
-/* 0 = v1 persistent cooperative kernel (grid barrier), 1 = v1 one launch per stage (debug cross-check),
- * 2 = v2: one 16-CTA cluster per 8 samples, cluster barriers only (experimental, slower),
- * 3 = EXPERIMENTAL cluster plan: set BEFORE ts_load_pixelcnn; 4-CTA clusters share a task's rows, split its K
- *     range and reduce through distributed shared memory (each CTA reads a quarter of the stage's activations) */
+/* PixelCNN executor: 0 (default) = grid-wide persistent cooperative kernel (grid barrier; batch tile 16 / 32 / 64 picked per
+ * launch), 1 = the same device code, one launch per stage (debug cross-check), 2 = cluster-resident executor: 16-CTA
+ * clusters own 4 / 8 samples, TMA weight ring, stage hand-over through DSMEM mbarriers, any batch size and both
+ * checkpoint geometries (dim 256 x 15 layers, dim 512 x 10 layers — the latter always runs here).  All three produce
+ * bit-identical logits. */
 int ts_set_pixelcnn_mode(ts_engine* e, int mode);
 /* Debug: per-stage, per-CTA globaltimer stamps of one latent row of the persistent kernel.  ts_pixelcnn_trace(e, row)
  * arms it (row < 0 disarms) for the following ts_pixelcnn_generate calls; ts_pixelcnn_trace_read copies

@@ -33,6 +33,10 @@ SYMBOLS = {
     "ts_load_face": (C.c_int, [C.c_void_p, C.POINTER(ts_tensor), C.c_int]),
     "ts_audio_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ts_latent_rows": (C.c_int, [C.c_int]),
+    "ts_vq_dim": (C.c_int, [C.c_void_p, C.c_int]),
+    "ts_load_smplx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ts_smplx_dims": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ts_smplx_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "ts_pixelcnn_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ts_pixelcnn_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

@@ -61,6 +61,7 @@ extern "C" void ts_engine_destroy(ts_engine* e) {
   delete e->conv;
   ts::face_destroy(e);
   ts::mfcc_destroy(e);
+  ts::smplx_destroy(e);
   delete e;
 }
 
@@ -177,6 +178,11 @@ extern "C" int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, 
   TS_API_END(e)
 }
 
+extern "C" int ts_vq_dim(ts_engine* e, int which) {
+  if (!e || which < 0 || which > 1 || !e->conv || !e->conv->vq[which].loaded) return 0;
+  return e->conv->vq[which].out_dim;
+}
+
 // ---- fused body path: audio encoder -> PixelCNN sampler -> two VQ decoders -------------------------
 extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise,
                                 int64_t* codes, float* poses, int B, int M, void* stream) {
@@ -195,9 +201,10 @@ extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* 
     int64_t* idx_c = e->ws.alloc<int64_t>((size_t)B * T * 2);  // [2][B][T] column-split copy
     pixelcnn_generate_act(e, a, label, noise, idx, nullptr, B, T, nullptr, 0, s);
     split_codes(e, idx, idx_c, B, T, codes, s);
+    const int c0 = e->conv->vq[0].out_dim, c1 = e->conv->vq[1].out_dim;   // 39 + 90 (axis-angle) or 78 + 180 (6-D)
     for (int w = 0; w < 2; ++w) {
       Act3 y = run_vq_decode(e, e->conv->vq[w], idx_c + (size_t)w * B * T, B, T, s);
-      act_to_btc(e, y, e->conv->vq[w].out_dim, poses, 129, w ? 39 : 0, s);
+      act_to_btc(e, y, e->conv->vq[w].out_dim, poses, c0 + c1, w ? c0 : 0, s);
     }
   };
   e->ws.begin_sizing();

@@ -137,6 +137,7 @@ struct ts_engine {
   ts::ConvStacks* conv = nullptr;
   ts::FaceNet* face = nullptr;
   void* mfcc_tables = nullptr;  // ts::MfccTables (mfcc.cu)
+  void* smplx = nullptr;        // ts::SmplxModel (lbs.cu)
   ts::Workspace ws;
   std::vector<void*> owned;  // device allocations that live as long as the engine
   // allocations of the weight sets, one slot per loadable module ("pixelcnn", "audioenc", "vq0", "vq1", "face"):

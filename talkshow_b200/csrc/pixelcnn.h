@@ -79,5 +79,6 @@ void split_codes(ts_engine* e, const int64_t* idx, int64_t* idx_c, int B, int T,
 void pixel_destroy(ts_engine* e);
 void face_destroy(ts_engine* e);
 void mfcc_destroy(ts_engine* e);
+void smplx_destroy(ts_engine* e);
 
 }  // namespace ts

@@ -162,6 +162,8 @@ class Engine:
         pre = None if pre_latents is None else self._dev(pre_latents, torch.int64)
         codes = torch.empty(B, T, 2, dtype=torch.int64, device=self.device)
         logits = torch.empty(2 * T, B, 2048, device=self.device) if want_logits else None
+        aud_c = aud.shape[1]
+        assert aud_c == 256, "AudioEncoder output has 256 channels"
         for b0 in range(0, B, PIX_TILE):
             b1 = min(B, b0 + PIX_TILE)
             nb = b1 - b0
@@ -191,11 +193,18 @@ class Engine:
                                               B, T, self._s()), "ts_pixelcnn_logits")
         return out
 
+    def vq_dim(self, which):
+        """pose channels of the loaded VQ-VAE: 39 / 90 (axis-angle), 78 / 180 (convert_to_6d)."""
+        c = int(self.L.ts_vq_dim(self.h, which))
+        if c <= 0:
+            raise RuntimeError("vq weights %d not loaded" % which)
+        return c
+
     def vq_decode(self, which, idx):
         """VQVAE.decode(latents=idx): [B,T] -> [B,C,4T]."""
         idx = self._dev(idx, torch.int64)
         B, T = idx.shape
-        C_ = 39 if which == 0 else 90
+        C_ = self.vq_dim(which)
         out = torch.empty(B, C_, 4 * T, device=self.device)
         self._check(self.L.ts_vq_decode(self.h, which, _lib.ptr(idx), _lib.ptr(out), B, T, self._s()), "ts_vq_decode")
         return out
@@ -224,7 +233,7 @@ class Engine:
         return out
 
     def body_generate(self, mfcc, label, noise, want_codes=True):
-        """fused s2g_body_pixel core: mfcc [B,64,M] -> (codes [B,T,2], poses [B,4T,129])."""
+        """fused s2g_body_pixel core: mfcc [B,64,M] -> (codes [B,T,2], poses [B,4T,C]), C = 129 (258 for 6-D)."""
         mfcc = self._dev(mfcc, torch.float32)
         label = self._dev(label, torch.int64)
         noise = self._dev(noise, torch.float32)
@@ -233,7 +242,7 @@ class Engine:
             label = label.expand(B).contiguous()
         T = self.latent_rows(M)
         codes = torch.empty(B, T, 2, dtype=torch.int64, device=self.device) if want_codes else None
-        poses = torch.empty(B, 4 * T, 129, device=self.device)
+        poses = torch.empty(B, 4 * T, self.vq_dim(0) + self.vq_dim(1), device=self.device)
         for b0 in range(0, B, PIX_TILE):
             b1 = min(B, b0 + PIX_TILE)
             full = (b1 - b0) == B

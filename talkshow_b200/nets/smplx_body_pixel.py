@@ -29,9 +29,9 @@ class TrainWrapper:
         self.audio = True
         self.composition = self.config.Model.composition
         self.bh_model = self.config.Model.bh_model
-        if self.convert_to_6d or not self.bh_model or not self.composition:
-            raise NotImplementedError("talkshow_b200 builds the shipped config/body_pixel.json geometry "
-                                      "(convert_to_6d=false, bh_model=true, composition=true)")
+        if not self.bh_model or not self.composition:
+            raise NotImplementedError("talkshow_b200 builds the bh_model=true, composition=true prior "
+                                      "(config/body_pixel.json); convert_to_6d selects the dim 512 x 10-layer geometry")
         self.engine = engine or shared_engine(self.device)
         self.noise_device = self.device      # 'cpu' reproduces the CPU reference's RNG stream
         self.noise_per_step = True
@@ -43,11 +43,14 @@ class TrainWrapper:
             self.load_vq_state_dict(ck)
 
     def init_params(self):
-        """nets/smplx_body_pixel.py:144-174 (3-D axis-angle layout): body 39 + hands 90."""
-        self.each_dim = [0, 39, 90, 100 if self.expression else 0]
-        self.dim_list = [0, 0, 0, 39, 129]
-        self.full_dim = 129
-        self.pose = 43
+        """nets/smplx_body_pixel.py:144-174: body 39 + hands 90 axis-angle dims, doubled for the 6-D layout
+        (convert_to_6d: the prior is pixelcnn(2048, 512, 10, ...) instead of (2048, 256, 15, ...), :49-52)."""
+        scale = 2 if self.convert_to_6d else 1
+        body, hand = 39 * scale, 90 * scale
+        self.each_dim = [0, body, hand, 100 if self.expression else 0]
+        self.dim_list = [0, 0, 0, body, body + hand]
+        self.full_dim = body + hand
+        self.pose = int(self.full_dim / round(3 * scale))
 
     # -- checkpoints -----------------------------------------------------------------------------
     def load_vq_state_dict(self, sd):

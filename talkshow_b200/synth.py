@@ -274,6 +274,16 @@ def body_pixel_checkpoint(seed=0):
     return {"generator": pixelcnn_state(seed), "audioencoder": audioenc_state(seed + 1)}
 
 
+def body_pixel_checkpoint_6d(seed=0):
+    """convert_to_6d geometry of nets/smplx_body_pixel.py:49-52: pixelcnn(2048, 512, 10, 4, True, True)."""
+    return {"generator": pixelcnn_state(seed + 20, dim=512, n_layers=10), "audioencoder": audioenc_state(seed + 1)}
+
+
+def body_vq_checkpoint_6d(seed=0):
+    """VQ-VAEs over the 6-D pose layout: body 78, hands 180 channels (nets/smplx_body_pixel.py:54-57 with scale 2)."""
+    return {"g_body": vqvae_state(78, seed + 22), "g_hand": vqvae_state(180, seed + 23)}
+
+
 def body_vq_checkpoint(seed=0):
     """... for s2g_body_vq, also the file ``config.Model.vq_path`` points to."""
     return {"g_body": vqvae_state(39, seed + 2), "g_hand": vqvae_state(90, seed + 3)}

@@ -153,6 +153,34 @@ def main():
                             vq_out=outv[::3].copy(), vq_seam=outv[56:64].copy())
         print("wrapper_cont", pred.shape, outv.shape)
 
+    # ---- 6-D geometry: pixelcnn(2048, 512, 10, ...) + VQ-VAEs over 78 / 180 channels (smplx_body_pixel.py:49-57) ----
+    if want("pixel_6d"):
+        vq6 = synth.body_vq_checkpoint_6d(0)
+        vq6_path = os.path.join(tmp, "vq6.pth")
+        torch.save({"generator": vq6}, vq6_path)
+        bp6 = synth.body_pixel_checkpoint_6d(0)
+        cfg6 = load_JsonConfig("config/body_pixel.json")
+        cfg6.Data.pose.convert_to_6d = True
+        cfg6.Model.vq_path = vq6_path
+        g6 = ref_bp.TrainWrapper(a, cfg6)
+        g6.load_state_dict(bp6)
+        assert g6.generator.dim == 512 and len(g6.generator.layers) == 10
+        mfcc = synth.synth_mfcc(1, 32, seed=611)                                   # T = 8 latent rows
+        ref_bp.get_mfcc_ta = lambda *aa, **kk: mfcc[0].transpose(0, 1).numpy()
+        torch.manual_seed(SAMPLER_SEED + 4)
+        pred = g6.infer_on_audio("synthetic.wav", id=torch.tensor([1]), fps=30, B=2)   # (2, 32, 258)
+        torch.manual_seed(SAMPLER_SEED + 4)
+        noise = draw_noise(16, 2)
+        torch.manual_seed(SAMPLER_SEED + 4)
+        audio = g6.audioencoder(mfcc.repeat(2, 1, 1)).unsqueeze(-1).repeat(1, 1, 1, 2)
+        lab = torch.tensor([1, 1])
+        lat = g6.generator.generate(lab, shape=[8, 2], batch_size=2, aud_feat=audio)
+        logits = g6.generator(lat, lab, audio)                                     # teacher-forced [2,2048,8,2]
+        np.savez_compressed(os.path.join(HERE, "pixel_6d.npz"), codes=lat.numpy(), pred=pred, logits=logits[:, :, [0, 3, 7], :].numpy(),
+                            logit_rows=np.array([0, 3, 7]), noise_fp=noise_fp(noise), sampler_seed=SAMPLER_SEED + 4,
+                            fp=np.array(list(synth.fingerprint(bp6).values())), fp_vq=np.array(list(synth.fingerprint(vq6).values())))
+        print("pixel_6d", lat[0, :3].tolist(), pred.shape)
+
     # ---- VQ roundtrip (config 2) -------------------------------------------------------------
     if want("vq_roundtrip"):
         gv = ref_vq.TrainWrapper(a, cfg_vq)

@@ -88,8 +88,8 @@ def test_vq_roundtrip_output(eng, ckpts):
 
 @pytest.mark.parametrize("mode", [1, 0, 2])
 def test_pixelcnn_teacher_forced_logits(eng, ckpts, mode):
-    """mode 1 = v1 one launch per stage (cross-check), 0 = v1 persistent cooperative kernel,
-    2 = v2 cluster-per-8-samples kernel."""
+    """mode 1 = grid-wide executor, one launch per stage (cross-check), 0 = grid-wide persistent cooperative kernel,
+    2 = cluster-resident executor (16-CTA clusters, TMA weight ring, DSMEM hand-over)."""
     eng.set_pixelcnn_mode(mode)
     try:
         sd = ckpts["pixel"]["generator"]
@@ -201,6 +201,50 @@ def test_body_generate_fused_b12(eng, ckpts):
     assert (poses.cpu() - ref_poses).abs().max().item() <= TOL
     # diversity: different noise rows give different sequences
     assert len({tuple(c.flatten().tolist()) for c in codes.cpu()}) > 1
+
+
+def test_pixelcnn_6d_geometry():
+    """f2: dim 512 x 10 layers (convert_to_6d, nets/smplx_body_pixel.py:49-52) runs on the cluster-resident executor:
+    reference-generated golden (codes, decoded 258-channel poses) + the oracle at a second shape with 5 samples."""
+    from talkshow_b200.engine import Engine
+
+    gold = _load("pixel_6d")
+    bp6, vq6 = synth.body_pixel_checkpoint_6d(0), synth.body_vq_checkpoint_6d(0)
+    e = Engine(0)
+    try:
+        e.load_pixelcnn(bp6["generator"])
+        e.load_audioenc(bp6["audioencoder"])
+        e.load_vq(0, vq6["g_body"])
+        e.load_vq(1, vq6["g_hand"])
+        assert (e.vq_dim(0), e.vq_dim(1)) == (78, 180)
+        mfcc = synth.synth_mfcc(1, 32, seed=611).repeat(2, 1, 1)
+        lab = torch.tensor([1, 1])
+        noise = draw_noise(16, 2, int(gold["sampler_seed"]))
+        codes, poses = e.body_generate(mfcc, lab, noise)
+        ref_codes, ref_poses = O.body_generate(bp6, vq6, mfcc, lab, noise=noise)
+        assert torch.equal(codes.cpu(), ref_codes)
+        assert poses.shape == (2, 32, 258) and (poses.cpu() - ref_poses).abs().max().item() <= TOL
+        if np.allclose(gold["noise_fp"], noise_fp(noise), rtol=0, atol=1e-9):
+            assert np.array_equal(codes.cpu().numpy(), gold["codes"])
+            assert np.abs(poses.cpu().numpy() - gold["pred"]).max() <= TOL
+        # teacher-forced logits
+        aud = O.audio_encoder(bp6["audioencoder"], mfcc)
+        ref_l = O.pixelcnn_forward(bp6["generator"], ref_codes, lab, aud.unsqueeze(-1).repeat(1, 1, 1, 2))
+        got_l = e.pixelcnn_logits(aud, lab, ref_codes).cpu()
+        err = (got_l - ref_l).abs().max().item()
+        print("6-D geometry teacher-forced logits max-abs err: %.3e (logit std %.2f)" % (err, ref_l.std().item()))
+        assert err <= TOL
+        # 5 samples, 4 speaker ids, 12 rows: two clusters of 4 samples
+        B, T = 5, 12
+        label = torch.tensor([0, 1, 2, 3, 1])
+        aud = O.audio_encoder(bp6["audioencoder"], synth.synth_mfcc(B, 4 * T, seed=612))
+        noise = draw_noise(2 * T, B, 613)
+        ref = O.pixelcnn_generate(bp6["generator"], label, T, B, aud.unsqueeze(-1).repeat(1, 1, 1, 2), noise=noise, window=None)
+        got = e.pixelcnn_generate(aud, label, noise)
+        assert torch.equal(got.cpu(), ref)
+    finally:
+        torch.cuda.synchronize()
+        e.close()
 
 
 def test_assemble_pose(eng):

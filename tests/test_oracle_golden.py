@@ -97,6 +97,27 @@ def test_wrapper_continuity(ckpts):
     assert np.abs(out[56:64] - g["vq_seam"]).max() <= 1e-6
 
 
+def test_pixel_6d_geometry():
+    """f2: the convert_to_6d geometry pixelcnn(2048, 512, 10, ...) + VQ-VAEs over 78 / 180 channels
+    (nets/smplx_body_pixel.py:49-57), reference wrapper run by make_golden.py --only pixel_6d."""
+    g = _load("pixel_6d")
+    bp6, vq6 = synth.body_pixel_checkpoint_6d(0), synth.body_vq_checkpoint_6d(0)
+    assert np.allclose(list(synth.fingerprint(bp6).values()), g["fp"], rtol=1e-12)
+    assert np.allclose(list(synth.fingerprint(vq6).values()), g["fp_vq"], rtol=1e-12)
+    noise = draw_noise(16, 2, int(g["sampler_seed"]))
+    if not _same_noise(g, noise):
+        pytest.skip("host RNG stream differs from the fixture machine")
+    mfcc = synth.synth_mfcc(1, 32, seed=611).repeat(2, 1, 1)
+    lab = torch.tensor([1, 1])
+    lat, pred = O.body_generate(bp6, vq6, mfcc, lab, noise=noise)
+    assert np.array_equal(lat.numpy(), g["codes"])
+    assert pred.shape == (2, 32, 258)
+    assert np.abs(pred.numpy() - g["pred"]).max() <= 1e-6
+    audio = O.audio_encoder(bp6["audioencoder"], mfcc).unsqueeze(-1).repeat(1, 1, 1, 2)
+    logits = O.pixelcnn_forward(bp6["generator"], lat, lab, audio)
+    assert np.abs(logits[:, :, g["logit_rows"].tolist(), :].numpy() - g["logits"]).max() <= 1e-5
+
+
 def test_vq_roundtrip(ckpts):
     g = _load("vq_roundtrip")
     poses = synth.synth_poses(2, 88)
