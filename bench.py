@@ -222,6 +222,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.barrier()
     eng = Engine(local_rank)
+    if world > 1:
+        eng.nccl_init(rank, world)                    # the pose all-gather runs inside the library (ts_allgather)
     wb = WholeBody(eng)
     ck = synthetic_ckpts()
     wb.load(ck["pixel"], ck["vq"], ck["face"])
@@ -275,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
                 self.noise()                         # keep the generator streams of the ranks in step
             else:
                 local = wb.generate(inputs[0], inputs[1], inputs[2], noise=self.noise())
-            return allgather_poses(local, self.Bg, world)
+            return allgather_poses(local, self.Bg, world, engine=eng)
 
         def step_device(self):
             return self.run(self.devt)

@@ -120,6 +120,16 @@ int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* 
  * data_utils/rotation_conversion.py:512-533,433-447.  d6 [n,6] -> aa [n,3] (device pointers). */
 int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, int64_t n, void* stream);
 
+/* ---- multi-GPU: the single collective of the path ------------------------------
+ * The reference generates diversity samples / clips in a Python loop (scripts/demo.py:195-204); here they are sharded
+ * one process per GPU and the [b,F,265] pose shards are all-gathered ONCE over NCCL (NVLink / NVSwitch).  NCCL is
+ * dlopen'ed (libnccl_path: e.g. torch's nvidia/nccl/lib/libnccl.so.2; NULL = "libnccl.so.2" from the loader path).
+ * Bootstrap: rank 0 calls ts_nccl_unique_id, ships the 128 bytes to the other ranks, every rank calls ts_nccl_init. */
+int ts_nccl_unique_id(ts_engine* e, const char* libnccl_path, void* id128_host);
+int ts_nccl_init(ts_engine* e, const char* libnccl_path, const void* id128_host, int rank, int world);
+/* out[world*count] = concat over ranks of in[count] (fp32 device pointers), on `stream`. */
+int ts_allgather(ts_engine* e, const float* in, float* out, int64_t count, void* stream);
+
 /* ---- batched SMPL-X evaluation ---------------------------------------------------
  * Replaces the per-frame smplx_model(...) calls of scripts/demo.py:122-152 (get_vertices) and data_utils/get_j.py:20-51
  * (get_joints): smplx 0.1.28 SMPLX.forward + lbs (use_pca=False, flat_hand_mean=False, 300 betas, 100 expression

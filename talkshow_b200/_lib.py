@@ -34,6 +34,9 @@ SYMBOLS = {
     "ts_audio_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ts_latent_rows": (C.c_int, [C.c_int]),
     "ts_vq_dim": (C.c_int, [C.c_void_p, C.c_int]),
+    "ts_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    "ts_nccl_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_int]),
+    "ts_allgather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ts_load_smplx": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ts_smplx_dims": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "ts_smplx_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtalkshow_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "gemm_tc.cu", "convstack.cu", "pixelcnn.cu", "face.cu", "mfcc.cu", "lbs.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemm_tc.cu", "convstack.cu", "pixelcnn.cu", "face.cu", "mfcc.cu", "lbs.cu", "collective.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr"]
@@ -42,7 +42,7 @@ def build(force=False, verbose=False):
         ok = ok and p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

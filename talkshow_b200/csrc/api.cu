@@ -62,6 +62,7 @@ extern "C" void ts_engine_destroy(ts_engine* e) {
   ts::face_destroy(e);
   ts::mfcc_destroy(e);
   ts::smplx_destroy(e);
+  ts::nccl_destroy(e);
   delete e;
 }
 

@@ -138,6 +138,7 @@ struct ts_engine {
   ts::FaceNet* face = nullptr;
   void* mfcc_tables = nullptr;  // ts::MfccTables (mfcc.cu)
   void* smplx = nullptr;        // ts::SmplxModel (lbs.cu)
+  void* nccl = nullptr;         // ts::NcclApi (collective.cu): dlopen'ed NCCL + this engine's communicator
   ts::Workspace ws;
   std::vector<void*> owned;  // device allocations that live as long as the engine
   // allocations of the weight sets, one slot per loadable module ("pixelcnn", "audioenc", "vq0", "vq1", "face"):

@@ -813,6 +813,175 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16p_kernel(con
   }
 }
 
+// Same arithmetic, KV-TILED for long clips (flash-attention style): the keys / values of a head are staged CH at a time,
+// every warp owns ONE 16-row query block and keeps its online-softmax state in registers across the chunks; grid =
+// (clip x head, query tiles of 16 x ATT_WARPS rows).  No limit on the clip length (the resident variant above needs the
+// whole sequence in shared memory: <= 384 frames = 12.8 s).
+__global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                                             float* __restrict__ out_lo, int T, int H, float scale, int CH) {
+  extern __shared__ __align__(16) uint32_t smw[];
+  const int Tp = CH;                               // keys resident per chunk (multiple of 64)
+  const int VW = Tp / 2 + 4;                       // V^T plane row stride in words (Tp halves + 8 pad)
+  uint32_t* Kh = smw;                              // [Tp][ATT_KW]   pairs (d, d+1)
+  uint32_t* Kl = Kh + (size_t)Tp * ATT_KW;
+  uint32_t* Vh = Kl + (size_t)Tp * ATT_KW;         // [64][VW]       pairs (key, key+1)
+  uint32_t* Vl = Vh + (size_t)64 * VW;
+  const int bh = blockIdx.x, b = bh / H, h = bh % H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int ld = 3 * H * 64;
+  const float* base = qkv + (size_t)b * T * ld + h * 64;
+  const int nrb = (T + 15) >> 4;
+  const int rb = blockIdx.y * ATT_WARPS + warp;      // one 16-row query block per warp
+  const bool live = rb < nrb;
+  {
+    const int ra = rb * 16 + g, rbw = ra + 8;
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      float2 x0 = make_float2(0.f, 0.f), x1 = x0, x2 = x0, x3 = x0;
+      if (ra < T) {
+        x0 = *reinterpret_cast<const float2*>(base + (size_t)ra * ld + ks * 16 + 2 * t);
+        x2 = *reinterpret_cast<const float2*>(base + (size_t)ra * ld + ks * 16 + 2 * t + 8);
+      }
+      if (rbw < T) {
+        x1 = *reinterpret_cast<const float2*>(base + (size_t)rbw * ld + ks * 16 + 2 * t);
+        x3 = *reinterpret_cast<const float2*>(base + (size_t)rbw * ld + ks * 16 + 2 * t + 8);
+      }
+      split_h2(x0.x * scale, x0.y * scale, qh[ks][0], ql[ks][0]);
+      split_h2(x1.x * scale, x1.y * scale, qh[ks][1], ql[ks][1]);
+      split_h2(x2.x * scale, x2.y * scale, qh[ks][2], ql[ks][2]);
+      split_h2(x3.x * scale, x3.y * scale, qh[ks][3], ql[ks][3]);
+    }
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
+    for (int c0 = 0; c0 < T; c0 += CH) {
+      if (c0) __syncthreads();                       // every warp is done with the previous chunk's planes
+    // fill K planes: one (key, d-pair) per iteration
+    for (int i = tid; i < Tp * 32; i += ATT_WARPS * 32) {
+      const int r = i >> 5, dp = i & 31;
+      float2 kv = make_float2(0.f, 0.f);
+      if (c0 + r < T) kv = *reinterpret_cast<const float2*>(base + (size_t)(c0 + r) * ld + H * 64 + 2 * dp);
+      uint32_t hi, lo;
+      split_h2(kv.x, kv.y, hi, lo);
+      Kh[r * ATT_KW + dp] = hi;
+      Kl[r * ATT_KW + dp] = lo;
+    }
+    // fill V^T planes: one (key-pair, d) per iteration, d fastest across lanes for coalesced global reads
+    for (int i = tid; i < (Tp / 2) * 64; i += ATT_WARPS * 32) {
+      const int kp = i >> 6, d = i & 63, r = 2 * kp;
+      const float v0 = c0 + r < T ? base[(size_t)(c0 + r) * ld + 2 * H * 64 + d] : 0.f;
+      const float v1 = c0 + r + 1 < T ? base[(size_t)(c0 + r + 1) * ld + 2 * H * 64 + d] : 0.f;
+      uint32_t hi, lo;
+      split_h2(v0, v1, hi, lo);
+      Vh[d * VW + kp] = hi;
+      Vl[d * VW + kp] = lo;
+    }
+      __syncthreads();
+      for (int kb = 0; live && kb < Tp && c0 + kb < T; kb += 64) {
+        float sc[8][4];
+  #pragma unroll
+        for (int nt = 0; nt < 8; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+        // b0 = K[key = kb + 8 nt + g][d = 16 ks + 2t, +1] = word (8 ks + t) of the key's row, b1 = word (8 ks + t + 4)
+        // (the three products of one accumulator are issued a whole pass apart, so dependent HMMAs never queue back to back)
+  #pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const int w = (kb + nt * 8 + g) * ATT_KW + ks * 8 + t;
+            bh0[nt] = Kh[w]; bh1[nt] = Kh[w + 4]; bl0[nt] = Kl[w]; bl1[nt] = Kl[w + 4];
+          }
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], ql[ks], bl0[nt], bl1[nt]);   // lo.lo: long rows sum thousands of keys, keep S exact to 2^-33
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], ql[ks], bh0[nt], bh1[nt]);
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], qh[ks], bl0[nt], bl1[nt]);
+  #pragma unroll
+          for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], qh[ks], bh0[nt], bh1[nt]);
+        }
+        float mx_a = -INFINITY, mx_b = -INFINITY;
+  #pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int key = c0 + kb + nt * 8 + 2 * t;
+          if (key >= T) sc[nt][0] = sc[nt][2] = -INFINITY;
+          if (key + 1 >= T) sc[nt][1] = sc[nt][3] = -INFINITY;
+          mx_a = fmaxf(mx_a, fmaxf(sc[nt][0], sc[nt][1]));
+          mx_b = fmaxf(mx_b, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+        const float ca = expf(m_a - mn_a), cb = expf(m_b - mn_b);
+        m_a = mn_a; m_b = mn_b;
+        l_a *= ca; l_b *= cb;
+  #pragma unroll
+        for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= ca; o[dt][1] *= ca; o[dt][2] *= cb; o[dt][3] *= cb; }
+        // b0 = V^T[d = 8 dt + g][keys kb + 16 j2 + 2t, +1] = word ((kb + 16 j2) / 2 + t) of row d, b1 = that + 4
+  #pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          if (c0 + kb + j2 * 16 >= T) break;
+          float p[8];
+  #pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            p[q * 4 + 0] = expf(sc[2 * j2 + q][0] - mn_a);
+            p[q * 4 + 1] = expf(sc[2 * j2 + q][1] - mn_a);
+            p[q * 4 + 2] = expf(sc[2 * j2 + q][2] - mn_b);
+            p[q * 4 + 3] = expf(sc[2 * j2 + q][3] - mn_b);
+          }
+          l_a += (p[0] + p[1]) + (p[4] + p[5]);
+          l_b += (p[2] + p[3]) + (p[6] + p[7]);
+          uint32_t ph[4], pl[4];
+          split_h2(p[0] * 1024.f, p[1] * 1024.f, ph[0], pl[0]);
+          split_h2(p[2] * 1024.f, p[3] * 1024.f, ph[1], pl[1]);
+          split_h2(p[4] * 1024.f, p[5] * 1024.f, ph[2], pl[2]);
+          split_h2(p[6] * 1024.f, p[7] * 1024.f, ph[3], pl[3]);
+          uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
+  #pragma unroll
+          for (int dt = 0; dt < 8; ++dt) {
+            const int w = (dt * 8 + g) * VW + (kb >> 1) + j2 * 8 + t;
+            bh0[dt] = Vh[w]; bh1[dt] = Vh[w + 4]; bl0[dt] = Vl[w]; bl1[dt] = Vl[w + 4];
+          }
+  #pragma unroll
+          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], pl, bh0[dt], bh1[dt]);
+  #pragma unroll
+          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], ph, bl0[dt], bl1[dt]);
+  #pragma unroll
+          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], ph, bh0[dt], bh1[dt]);
+        }
+      }
+    }
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+    l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+    l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+    const float ia = 1.0f / (l_a * 1024.f), ib = 1.0f / (l_b * 1024.f);
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = half ? rbw : ra;
+        if (!live || row >= T) continue;
+        const float inv = half ? ib : ia;
+        const float v0 = o[dt][half * 2] * inv, v1 = o[dt][half * 2 + 1] * inv;
+        const size_t at = ((size_t)b * T + row) * (H * 64) + h * 64 + dt * 8 + 2 * t;
+        if (out_lo) {
+          const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
+          *reinterpret_cast<float2*>(out + at) = make_float2(h0, h1);
+          *reinterpret_cast<float2*>(out_lo + at) = make_float2(v0 - h0, v1 - h1);
+        } else {
+          *reinterpret_cast<float2*>(out + at) = make_float2(v0, v1);
+        }
+      }
+    }
+  }
+}
+
+
 static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
   static const int att_mode = getenv("TS_ATT_MMA") ? atoi(getenv("TS_ATT_MMA")) : 3;   // A/B switch: 0 FFMA, 1 tf32 MMA, 2 fp16-split MMA, 3 fp16-split MMA with K/V split once per CTA
@@ -826,6 +995,15 @@ static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo,
       TS_CUDA(cudaGetLastError());
       return;
     }
+    // longer than 12.8 s: the same arithmetic, keys / values staged 320 at a time (no length limit)
+    const int CH = 320;
+    const size_t smem16t = ((size_t)2 * CH * ATT_KW + (size_t)2 * 64 * (CH / 2 + 4)) * sizeof(uint32_t);
+    TS_CUDA(cudaFuncSetAttribute(attention_mma16t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16t));
+    const int nrb = (T + 15) / 16;
+    attention_mma16t_kernel<<<dim3(B * H, cdiv(nrb, ATT_WARPS)), ATT_WARPS * 32, smem16t, s>>>(qkv, out, out_lo, T, H, 0.125f, CH);
+    e->launches++;
+    TS_CUDA(cudaGetLastError());
+    return;
   }
   if (att_mode == 2 || att_mode == 3) {
     const int Tp64 = (T + 63) & ~63;

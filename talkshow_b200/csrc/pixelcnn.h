@@ -80,5 +80,6 @@ void pixel_destroy(ts_engine* e);
 void face_destroy(ts_engine* e);
 void mfcc_destroy(ts_engine* e);
 void smplx_destroy(ts_engine* e);
+void nccl_destroy(ts_engine* e);
 
 }  // namespace ts

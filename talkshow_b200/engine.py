@@ -253,6 +253,43 @@ class Engine:
                 "ts_body_generate")
         return codes, poses
 
+    # -- the single collective of the path, inside the library (ts_allgather over a dlopen'ed NCCL) ----------------
+    @staticmethod
+    def _libnccl_path():
+        import glob
+        import os
+
+        base = os.path.dirname(os.path.dirname(torch.__file__))
+        hits = glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so*"))
+        return (hits[0] if hits else "libnccl.so.2").encode()
+
+    def nccl_init(self, rank, world, group=None):
+        """Create this engine's NCCL communicator.  The 128-byte unique id is made on rank 0 and broadcast with
+        torch.distributed (any backend: it is 128 bytes of host data), every rank then joins."""
+        import torch.distributed as dist
+
+        path = self._libnccl_path()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            self._check(self.L.ts_nccl_unique_id(self.h, path, buf.data_ptr()), "ts_nccl_unique_id")
+        if world > 1:
+            obj = [buf.numpy().tobytes()]
+            dist.broadcast_object_list(obj, src=0, group=group)
+            buf = torch.frombuffer(bytearray(obj[0]), dtype=torch.uint8).clone()
+        self._check(self.L.ts_nccl_init(self.h, path, buf.data_ptr(), rank, world), "ts_nccl_init")
+        self.nccl_world = world
+        return self
+
+    def allgather(self, local):
+        """local [n, ...] fp32 (same shape on every rank) -> [world * n, ...] through ts_allgather (NCCL, current stream)."""
+        local = self._dev(local, torch.float32)
+        world = getattr(self, "nccl_world", 0)
+        if not world:
+            raise RuntimeError("Engine.nccl_init was not called")
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), device=self.device)
+        self._check(self.L.ts_allgather(self.h, _lib.ptr(local), _lib.ptr(out), local.numel(), self._s()), "ts_allgather")
+        return out
+
     def rot6d_to_axis_angle(self, d6):
         """matrix_to_axis_angle(rotation_6d_to_matrix(d6)) (rotation_conversion.py:512-533,433-447): [...,6] -> [...,3]."""
         d6 = self._dev(d6, torch.float32)

@@ -71,7 +71,7 @@ class WholeBody:
             dev = lambda t: t[lo:hi].to(self.device, non_blocking=True)
             local = self.generate(dev(mfcc), dev(wave), dev(label), noise=noise_full[:, lo:hi].to(self.device).contiguous(),
                                   stand=stand)
-        return allgather_poses(local, B, world, group=group) if gather else local
+        return allgather_poses(local, B, world, group=group, engine=self.e) if gather else local
 
     def generate_host(self, mfcc_host, wave_host, label_host, out_host=None, **kw):
         """Public end-to-end call with HOST buffers (pinned for async copies): H2D inputs, generate,
@@ -87,9 +87,11 @@ class WholeBody:
         return out_host
 
 
-def allgather_poses(local, B_total, world, group=None):
+def allgather_poses(local, B_total, world, group=None, engine=None):
     """ONE all-gather of the pose tensor over NCCL (NVLink/NVSwitch).  local [b,F,265] -> [B_total,F,265].
-    Uneven shards are padded to the largest shard for the collective and trimmed afterwards."""
+    Uneven shards are padded to the largest shard for the collective and trimmed afterwards.  With an ``engine`` whose
+    communicator was created (``Engine.nccl_init``) the collective is the library's own ``ts_allgather``; otherwise
+    torch.distributed's ``all_gather_into_tensor`` (NCCL on GPUs, gloo in the CPU tests)."""
     import torch.distributed as dist
 
     if world == 1:
@@ -98,8 +100,11 @@ def allgather_poses(local, B_total, world, group=None):
     if local.shape[0] < bmax:
         pad = torch.zeros((bmax - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         local = torch.cat([local, pad], 0)
-    out = torch.empty((world * bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    if engine is not None and getattr(engine, "nccl_world", 0) == world:
+        out = engine.allgather(local.contiguous())
+    else:
+        out = torch.empty((world * bmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
     if B_total == world * bmax:
         return out
     parts = []

@@ -345,3 +345,19 @@ def test_rot6d_to_axis_angle(eng):
 
     d = rotmat(got[~ok]) @ rotmat(ref[~ok]).transpose(1, 2) - torch.eye(3, dtype=torch.float64)
     assert d.abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("frames", [500, 1600, 3100])
+def test_face_long_clips(face_eng, ckpts, frames):
+    """Clips longer than 12.8 s (384 frames) take the KV-tiled attention kernel by default dispatch (the resident
+    kernel keeps a head's whole K/V in shared memory); 3100 frames = 103 s is past the old 100 s limit.  Same 1e-4 bar."""
+    N = frames * 16000 // 30 + 7
+    wave = synth.synth_wave(1, N, seed=frames)
+    ids = torch.nn.functional.one_hot(torch.tensor([3]), 4).float()
+    torch.set_num_threads(min(32, torch.get_num_threads()))
+    ref = O.face_forward(ckpts["face"]["generator"], wave, ids, frames)
+    got = face_eng.face_forward(wave, ids, frames).cpu()
+    err = (got - ref).abs().max().item()
+    print("face %d frames (%.0f s) max-abs err vs oracle: %.3e" % (frames, frames / 30, err))
+    assert got.shape == (1, frames, 103)
+    assert err <= TOL

@@ -201,3 +201,54 @@ def test_edge_shapes(ckpts):
     assert torch.equal(c[64:].cpu(), ref_c)
     torch.cuda.synchronize()
     e.close()
+
+
+def test_demo_flow_matches_reference_flow(ckpts, tmp_path, monkeypatch):
+    """The body of the reference's scripts/demo.py (:158-246: face pass, num_sample body samples, jaw | body | expression ->
+    part2full -> (num_sample*F, 265) .npy) through talkshow_b200.scripts.demo with checkpoint FILES, a wav file and the
+    reference's command line, against the oracle run sample by sample with the reference's RNG order."""
+    from scipy.io import wavfile
+
+    from talkshow_b200.data_utils.utils import load_wav, mfcc_from_wave
+    from talkshow_b200.scripts import demo
+    from talkshow_b200.trainer.options import parse_args
+
+    sec, nsamp, spk = 3, 3, 2
+    x = (synth.synth_wave(1, 16000 * sec, seed=41)[0].numpy() * 20000).astype(np.int16)
+    wav = str(tmp_path / "clip one.wav")
+    wavfile.write(wav, 16000, x)
+    torch.save({"generator": ckpts["pixel"]}, str(tmp_path / "body.pth"))
+    torch.save({"generator": ckpts["face"]}, str(tmp_path / "face.pth"))
+    torch.save({"generator": ckpts["vq"]}, str(tmp_path / "vq.pth"))
+    args = parse_args().parse_args(["--config_file", os.path.join(ROOT, "config", "body_pixel.json"), "--infer", "--audio_file", wav,
+                                    "--id", str(spk), "--num_sample", str(nsamp), "--body_model_path", str(tmp_path / "body.pth"),
+                                    "--face_model_path", str(tmp_path / "face.pth")])
+    assert args.body_model_name == "s2g_body_pixel" and args.face_model_name == "s2g_face"      # reference defaults
+    config = _cfg("body_pixel")
+    config.Model.vq_path = str(tmp_path / "vq.pth")
+    g_body = demo.init_model(args.body_model_name, args.body_model_path, args, config)
+    g_face = demo.init_model(args.face_model_name, args.face_model_path, args, _cfg("face"))
+    g_body.noise_device = "cpu"
+    g_body.device_mfcc = False            # the oracle sees the host torchaudio features
+    monkeypatch.chdir(tmp_path)
+    seed = 321
+    torch.manual_seed(seed)
+    result_list, verts = demo.infer(g_body, g_face, None, None, config, args)
+    assert verts is None and len(result_list) == nsamp
+    # oracle, the reference's order: face once, then one body sample after the other from the same generator
+    audio, sr = load_wav(wav)
+    frame = audio.shape[1] * 30 // 16000
+    face = O.face_forward(ckpts["face"]["generator"], audio, torch.zeros(1, 4), frame)[0]
+    mfcc = torch.from_numpy(mfcc_from_wave(audio, sr, sr=22000, fps=30).T.copy())[None]
+    T = O.latent_rows(mfcc.shape[2])
+    torch.manual_seed(seed)
+    for i in range(nsamp):
+        noise = torch.stack([torch.empty(1, 2048).exponential_(1) for _ in range(2 * T)])
+        _, body = O.body_generate(ckpts["pixel"], ckpts["vq"], mfcc, torch.tensor([spk]), noise=noise, window=18)
+        ref = O.assemble_pose(face, body[0])
+        assert result_list[i].shape == ref.shape == (frame, 265)
+        assert (result_list[i].cpu() - ref).abs().max().item() <= 1e-4
+    saved = np.load(str(tmp_path / "visualise" / "video" / config.Log.name / "clip one.npy"))
+    assert saved.shape == (nsamp * frame, 265)                       # scripts/demo.py:239-245
+    assert np.array_equal(saved, np.concatenate([r.cpu().numpy() for r in result_list], 0))
+    assert not np.array_equal(saved[:frame], saved[frame:2 * frame])      # diversity samples differ
