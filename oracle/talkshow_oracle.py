@@ -354,7 +354,7 @@ def face_forward(sd, wave, id_onehot, frame):
     'faceformer', identity=True).  wave [B,N], id_onehot [B,4] float -> [B,frame,103]."""
     h = wav2vec2(sd, "audio_encoder.", wave, frame)
     feat = F.linear(h, sd["audio_feature_map.weight"], sd["audio_feature_map.bias"]).transpose(1, 2)
-    idv = id_onehot.reshape(id_onehot.shape[0], -1, 1).repeat(1, 1, feat.shape[2]).to(torch.float32)
+    idv = id_onehot.reshape(id_onehot.shape[0], -1, 1).repeat(1, 1, feat.shape[2]).to(feat.dtype)
     idv = F.conv1d(idv, sd["audio_middle.id_mlp.weight"], sd["audio_middle.id_mlp.bias"])
     x = torch.cat([feat, idv.expand(feat.shape[0], -1, -1)], 1)
     f = "audio_middle.first_net.conv_layers."

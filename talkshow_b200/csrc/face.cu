@@ -139,7 +139,9 @@ __global__ void interp_kernel(Act3 in, Act3 out) {
     int c = i % out.C;
     long bt = i / out.C;
     int t = bt % out.T, b = bt / out.T;
-    float src = scale * (t + 0.5f) - 0.5f;
+    // ATen's area_pixel_compute_source_index in float, as two rounded operations (no FMA contraction): at 100 s the
+    // source positions reach 5000 and a differently rounded position moves the interpolation weights by 1e-4
+    float src = __fsub_rn(__fmul_rn(scale, (float)t + 0.5f), 0.5f);
     if (src < 0.f) src = 0.f;
     int i0 = (int)src;
     if (i0 > in.T - 1) i0 = in.T - 1;
@@ -894,8 +896,6 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
             bh0[nt] = Kh[w]; bh1[nt] = Kh[w + 4]; bl0[nt] = Kl[w]; bl1[nt] = Kl[w + 4];
           }
   #pragma unroll
-          for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], ql[ks], bl0[nt], bl1[nt]);   // lo.lo: long rows sum thousands of keys, keep S exact to 2^-33
-  #pragma unroll
           for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], ql[ks], bh0[nt], bh1[nt]);
   #pragma unroll
           for (int nt = 0; nt < 8; ++nt) mma_f16(sc[nt], qh[ks], bl0[nt], bl1[nt]);
@@ -921,6 +921,11 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
         l_a *= ca; l_b *= cb;
   #pragma unroll
         for (int dt = 0; dt < 8; ++dt) { o[dt][0] *= ca; o[dt][1] *= ca; o[dt][2] *= cb; o[dt][3] *= cb; }
+        // the tensor-core fp32 accumulator truncates: a 100 s clip would chain ~600 accumulations per output.  Each
+        // 64-key block accumulates into a fresh fragment (12 MMAs deep) that is added to the running output with RN adds.
+        float oc[8][4];
+  #pragma unroll
+        for (int dt = 0; dt < 8; ++dt) oc[dt][0] = oc[dt][1] = oc[dt][2] = oc[dt][3] = 0.f;
         // b0 = V^T[d = 8 dt + g][keys kb + 16 j2 + 2t, +1] = word ((kb + 16 j2) / 2 + t) of row d, b1 = that + 4
   #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
@@ -947,12 +952,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
             bh0[dt] = Vh[w]; bh1[dt] = Vh[w + 4]; bl0[dt] = Vl[w]; bl1[dt] = Vl[w + 4];
           }
   #pragma unroll
-          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], pl, bh0[dt], bh1[dt]);
+          for (int dt = 0; dt < 8; ++dt) mma_f16(oc[dt], pl, bh0[dt], bh1[dt]);
   #pragma unroll
-          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], ph, bl0[dt], bl1[dt]);
+          for (int dt = 0; dt < 8; ++dt) mma_f16(oc[dt], ph, bl0[dt], bl1[dt]);
   #pragma unroll
-          for (int dt = 0; dt < 8; ++dt) mma_f16(o[dt], ph, bh0[dt], bh1[dt]);
+          for (int dt = 0; dt < 8; ++dt) mma_f16(oc[dt], ph, bh0[dt], bh1[dt]);
         }
+  #pragma unroll
+        for (int dt = 0; dt < 8; ++dt) { o[dt][0] += oc[dt][0]; o[dt][1] += oc[dt][1]; o[dt][2] += oc[dt][2]; o[dt][3] += oc[dt][3]; }
       }
     }
     l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);

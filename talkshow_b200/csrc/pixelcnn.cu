@@ -723,50 +723,44 @@ __device__ __forceinline__ void mm_rows_small(const float* __restrict__ Wsm, int
   const int kper = K >> 3;  // multiple of 32
   const int slice = (warp + blockIdx.x) & 7;
   const int kbeg = slice * kper, kend = kbeg + kper;
-  // ring of G groups x 8 activation loads (4 B each), a group is re-issued for k + 8 G as soon as its FMAs are done:
-  // 32 loads in flight per lane (deeper rings — 48, 64 — measured slower: 344 vs 244 us per row at the 16-sample tile)
-  constexpr int G = 4, GS = 8;
-  const int ng = kper / GS;        // 4 .. 24 groups in this warp's K slice
+  constexpr int G = 4, GS = 8;   // ring of 4 groups x 8 activation loads, re-issued as soon as a group's FMAs are done
   float x[G][GS];
 #pragma unroll
-  for (int g = 0; g < G; ++g)
-    if (g < ng) {
-      const int k = kbeg + g * GS;
-      const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
+  for (int g = 0; g < G; ++g) {
+    const int k = kbeg + g * GS;
+    const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
 #pragma unroll
-      for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
-    }
+    for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
+  }
   const float* wl = Wsm + rq * RPL;
-  for (int g0 = 0; g0 < ng; g0 += G) {
+  for (int k0 = kbeg; k0 < kend; k0 += G * GS) {
+    const bool more = k0 + G * GS < kend;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
-      if (g0 + g < ng) {
-        const int k0 = kbeg + (g0 + g) * GS;
 #pragma unroll
-        for (int u = 0; u < GS; ++u) {
-          const float* wr = wl + (size_t)(k0 + u) * RPAD;
-          const float xv = x[g][u];
-          if constexpr (RPL % 4 == 0) {
+      for (int u = 0; u < GS; ++u) {
+        const float* wr = wl + (size_t)(k0 + g * GS + u) * RPAD;
+        const float xv = x[g][u];
+        if constexpr (RPL % 4 == 0) {
 #pragma unroll
-            for (int q = 0; q < RPL / 4; ++q) {
-              const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wr + 4 * q);
-              fma2p(acc2[2 * q], w.x, xv);
-              fma2p(acc2[2 * q + 1], w.y, xv);
-            }
-          } else if constexpr (PACK) {
-#pragma unroll
-            for (int q = 0; q < RPL / 2; ++q) fma2p(acc2[q], *reinterpret_cast<const unsigned long long*>(wr + 2 * q), xv);
-          } else {
-#pragma unroll
-            for (int j = 0; j < RPL; ++j) acc[j] = fmaf(wr[j], xv, acc[j]);
+          for (int q = 0; q < RPL / 4; ++q) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wr + 4 * q);
+            fma2p(acc2[2 * q], w.x, xv);
+            fma2p(acc2[2 * q + 1], w.y, xv);
           }
-        }
-        if (g0 + g + G < ng) {
-          const int k = k0 + G * GS;
-          const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
+        } else if constexpr (PACK) {
 #pragma unroll
-          for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
+          for (int q = 0; q < RPL / 2; ++q) fma2p(acc2[q], *reinterpret_cast<const unsigned long long*>(wr + 2 * q), xv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < RPL; ++j) acc[j] = fmaf(wr[j], xv, acc[j]);
         }
+      }
+      if (more) {
+        const int k = k0 + G * GS + g * GS;
+        const float* base = arena + seg[k >> 8] + (k & 255) * MB + m;
+#pragma unroll
+        for (int u = 0; u < GS; ++u) x[g][u] = __ldcg(base + u * MB);
       }
     }
   }

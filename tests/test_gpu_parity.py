@@ -350,14 +350,26 @@ def test_rot6d_to_axis_angle(eng):
 @pytest.mark.parametrize("frames", [500, 1600, 3100])
 def test_face_long_clips(face_eng, ckpts, frames):
     """Clips longer than 12.8 s (384 frames) take the KV-tiled attention kernel by default dispatch (the resident
-    kernel keeps a head's whole K/V in shared memory); 3100 frames = 103 s is past the old 100 s limit.  Same 1e-4 bar."""
+    kernel keeps a head's whole K/V in shared memory); 3100 frames = 103 s is past the old 100 s limit.  Bar: 1e-4 against
+    the fp32 CPU path up to 53 s.  At 103 s two fp32 evaluations no longer agree to 1e-4 among themselves (sums over
+    3100 keys / frames): there the engine is held to 1e-4 against a FLOAT64 evaluation of the same restatement and to
+    1e-4 plus the CPU path's own distance from float64 against the fp32 CPU path."""
     N = frames * 16000 // 30 + 7
     wave = synth.synth_wave(1, N, seed=frames)
     ids = torch.nn.functional.one_hot(torch.tensor([3]), 4).float()
     torch.set_num_threads(min(32, torch.get_num_threads()))
-    ref = O.face_forward(ckpts["face"]["generator"], wave, ids, frames)
+    sd = ckpts["face"]["generator"]
+    ref = O.face_forward(sd, wave, ids, frames)
     got = face_eng.face_forward(wave, ids, frames).cpu()
     err = (got - ref).abs().max().item()
     print("face %d frames (%.0f s) max-abs err vs oracle: %.3e" % (frames, frames / 30, err))
     assert got.shape == (1, frames, 103)
-    assert err <= TOL
+    if frames <= 2000:
+        assert err <= TOL
+    else:
+        sd64 = {k: (v.double() if torch.is_floating_point(v) else v) for k, v in sd.items()}
+        ref64 = O.face_forward(sd64, wave.double(), ids.double(), frames)
+        e_got, e_ref = (got.double() - ref64).abs().max().item(), (ref.double() - ref64).abs().max().item()
+        print("  vs float64: engine %.3e, fp32 CPU path %.3e" % (e_got, e_ref))
+        assert e_got <= TOL
+        assert err <= TOL + e_ref
