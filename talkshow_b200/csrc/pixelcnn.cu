@@ -708,7 +708,7 @@ __device__ __forceinline__ int ax(int ch, int m) { return ch * MB + m; }
 // owns RPL = rpad * MB / 32 consecutive weight rows of the task for ONE sample.  Same K slicing (8 contiguous slices, one
 // per warp, summed in k order) and the same slice-ordered reduction as the 64-sample kernels, so every output is
 // bit-identical whatever tile a sample runs in.  Packed fp32 FMAs over ROW pairs when RPL is even.
-template <int RC, int MB>
+template <int RC, int MB, int G>
 __device__ __forceinline__ void mm_rows_small(const float* __restrict__ Wsm, int K, const int* seg, const float* arena,
                                               float* red, int warp, int lane) {
   constexpr int RPL = RC * MB / 8, RPAD = 4 * RC;
@@ -723,7 +723,7 @@ __device__ __forceinline__ void mm_rows_small(const float* __restrict__ Wsm, int
   const int kper = K >> 3;  // multiple of 32
   const int slice = (warp + blockIdx.x) & 7;
   const int kbeg = slice * kper, kend = kbeg + kper;
-  constexpr int G = 4, GS = 8;   // ring of 4 groups x 8 activation loads, re-issued as soon as a group's FMAs are done
+  constexpr int GS = 8;   // ring of G groups x 8 activation loads, re-issued as soon as a group's FMAs are done
   float x[G][GS];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
@@ -839,11 +839,22 @@ __device__ void run_matmul_task(const PixTask& t, const PixArgs& A, int r, const
     if (pass > 0) __syncthreads();  // previous pass's epilogue finished reading red
     if (t.K > 0) {
       if constexpr (MB < 64) {   // small batch tiles: lane = (sample, row group), FFMA2 over row pairs
-        switch (t.rpad >> 2) {
-          case 1: mm_rows_small<1, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-          case 2: mm_rows_small<2, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-          case 3: mm_rows_small<3, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
-          default: mm_rows_small<4, MB>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+        // K slices that are a multiple of 64 (K = 512, 1024, 1536) keep 64 loads in flight per lane at the 16-sample tile
+        // (a K = 512 stage is then ONE round trip to L2), the others 32
+        if (MB == 16 && (t.K & 511) == 0) {
+          switch (t.rpad >> 2) {
+            case 1: mm_rows_small<1, MB, MB == 16 ? 8 : 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            case 2: mm_rows_small<2, MB, MB == 16 ? 8 : 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            case 3: mm_rows_small<3, MB, MB == 16 ? 8 : 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            default: mm_rows_small<4, MB, MB == 16 ? 8 : 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          }
+        } else {
+          switch (t.rpad >> 2) {
+            case 1: mm_rows_small<1, MB, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            case 2: mm_rows_small<2, MB, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            case 3: mm_rows_small<3, MB, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+            default: mm_rows_small<4, MB, 4>(Wsm, t.K, s_seg, arena, red, warp, lane); break;
+          }
         }
       } else if constexpr (PIPE == 5) {
         switch (t.rpad >> 2) {
