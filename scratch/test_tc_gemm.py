@@ -15,7 +15,7 @@ torch.manual_seed(0)
 for (M,N,K) in [(128,128,32),(128,128,64),(300,200,96),(4096,512,1536),(1000,64,512),(777,3072,768)]:
     A = torch.randn(M,K,device='cuda'); W = torch.randn(N,K,device='cuda')/K**0.5; b = torch.randn(N,device='cuda')
     ref = (A.double() @ W.double().t() + b.double())
-    for mode in (0,1):
+    for mode in (0,1,2):
         try:
             out = run(mode, A, W, b)
             err = (out.double()-ref).abs().max().item()
@@ -25,8 +25,8 @@ for (M,N,K) in [(128,128,32),(128,128,64),(300,200,96),(4096,512,1536),(1000,64,
 # timing
 M,N,K = 65536, 768, 3072
 A = torch.randn(M,K,device='cuda'); W = torch.randn(N,K,device='cuda')/K**0.5; b = torch.zeros(N,device='cuda')
-for mode in (0,1):
+for mode in (0,1,2):
     out = run(mode, A, W, b)
     t0=torch.cuda.Event(enable_timing=True); t1=torch.cuda.Event(enable_timing=True)
-    t0.record(); out = run(mode, A, W, b); t1.record(); torch.cuda.synchronize()
+    torch.cuda.synchronize(); t0.record(); out = run(mode, A, W, b); t1.record(); torch.cuda.synchronize()
     print("mode %d: %.2f ms (incl. split+alloc for mode 1) -> %.1f TFLOP/s" % (mode, t0.elapsed_time(t1), 2*M*N*K/t0.elapsed_time(t1)/1e9))

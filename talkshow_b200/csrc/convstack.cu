@@ -214,7 +214,7 @@ static Act3 run_up(ts_engine* e, const Layer& ev, const Layer& od, const Act3& x
 
 // q: quantised latents [B,T,64] channel-last -> decoder output Act3 [B,4T,C]
 Act3 run_decoder(ts_engine* e, const VQNet& v, const Act3& q, cudaStream_t s) {
-  const bool tc = e->use_tc;
+  const bool tc = e->use_tc && !(e->tc_pair && e->tc_onchip);   // activations stored split (hi, lo) only for the pre-split kernels
   Act3 h = new_act(e, q.B, q.T, 1024, 1, s, tc);
   conv_auto(e, v.aft_vq, q, 1, 1, 0, h, q.T, ACT_NONE, nullptr, s);
   h = run_stack(e, v.d1, h, s, tc);

@@ -1066,7 +1066,7 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   // ---- wav2vec2 feature extractor ---------------------------------------------------------
   int T = (N - 10) / 5 + 1;
   double* stats = e->ws.alloc<double>((size_t)B * 512 * 2);
-  const bool tc = e->use_tc;
+  const bool tc = e->use_tc && !(e->tc_pair && e->tc_onchip);   // activations stored split (hi, lo) only for the pre-split kernels
   Act3 h = new_act(e, B, T, 512, 0, s, tc, T & 1);     // rows per batch even for the stride-2 convs
   if (!e->ws.sizing) {
     TS_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 512 * 2 * sizeof(double), s));

@@ -398,6 +398,12 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on th
                : "memory");
 }
 
+// ONCHIP = true (round 2, default): the operands arrive as PLAIN fp32 — one TMA box per operand and k-block instead of two,
+// i.e. half the L2 -> shared-memory bytes that profiles/r01c identified as the limiter — and the two otherwise idle warps
+// of warpgroup 0 split them in shared memory: lo = x - (x & 0xffffe000) is written to the `lo` tile at the SAME offset
+// (elementwise, so the 128 B swizzle is irrelevant), x itself is truncated in place to the `hi` value.  The converters of
+// both CTAs then arrive on the leader's `full` barrier (generic -> async proxy fence first), which the MMA issuer waits on.
+template <bool ONCHIP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                 const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P) {
@@ -408,6 +414,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
   uint64_t* tfull = empty + T2_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* raw = tempty + 4;                       // ONCHIP: this CTA's plain operand boxes have landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair
   // 1-D grid, (2,1,1) clusters: blockIdx.x = 2 * (n_tile + tiles_n * m_pair) + member  (P.cn carries tiles_n);
@@ -417,7 +424,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
   const int nk = P.taps * P.cblocks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < T2_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    // full: TMA bytes of both CTAs (pre-split operands) or the 2 x 2 converter warps of the pair (ONCHIP)
+    for (int i = 0; i < T2_STAGES; ++i) { mb_init(&full[i], ONCHIP ? 4 : 1); mb_init(&empty[i], 1); mb_init(&raw[i], 1); }
     mb_init(&tfull[0], 1); mb_init(&tfull[1], 1);
     mb_init(&tempty[0], 2 * TC_EPI_WARPS); mb_init(&tempty[1], 2 * TC_EPI_WARPS);   // epilogue warps of both CTAs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -461,14 +469,20 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
         mb_wait(&empty[st], ph ^ 1);
         const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
         unsigned char* base = smem + st * T2_STAGE_BYTES;
-        if (rank == 0) mb_expect(&full[st], 2 * T2_STAGE_BYTES);            // bytes of both CTAs land on the leader's barrier
-        const uint32_t lbar = s_u32(&full[st]) & 0xFEFFFFFFu;               // peer bit cleared -> CTA 0 of the pair
         const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
-        tma_3d_2sm(base, &mA_hi, c0, c1, c2, lbar);
-        tma_3d_2sm(base + TC_A_BYTES, &mA_lo, c0, c1, c2, lbar);
         const int kcol = tap * P.C + cb * TC_BK, nrow = n0 + (int)rank * (TC_BN / 2);
-        tma_2d_2sm(base + 2 * TC_A_BYTES, &mB_hi, kcol, nrow, lbar);
-        tma_2d_2sm(base + 2 * TC_A_BYTES + T2_BHALF, &mB_lo, kcol, nrow, lbar);
+        if constexpr (ONCHIP) {
+          mb_expect(&raw[st], TC_A_BYTES + T2_BHALF);                       // this CTA's two plain boxes, on its own barrier
+          tma_3d(base, &mA_hi, c0, c1, c2, &raw[st]);
+          tma_2d(base + 2 * TC_A_BYTES, &mB_hi, kcol, nrow, &raw[st]);
+        } else {
+          if (rank == 0) mb_expect(&full[st], 2 * T2_STAGE_BYTES);          // bytes of both CTAs land on the leader's barrier
+          const uint32_t lbar = s_u32(&full[st]) & 0xFEFFFFFFu;             // peer bit cleared -> CTA 0 of the pair
+          tma_3d_2sm(base, &mA_hi, c0, c1, c2, lbar);
+          tma_3d_2sm(base + TC_A_BYTES, &mA_lo, c0, c1, c2, lbar);
+          tma_2d_2sm(base + 2 * TC_A_BYTES, &mB_hi, kcol, nrow, lbar);
+          tma_2d_2sm(base + 2 * TC_A_BYTES + T2_BHALF, &mB_lo, kcol, nrow, lbar);
+        }
       }
       __syncwarp();
     }
@@ -497,7 +511,37 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
         if (kin == TC_CHUNK - 1 || kb == nk - 1) umma2_commit(&tfull[buf]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    if constexpr (ONCHIP) {
+      // ===== converter warps 2, 3 (64 threads) of BOTH CTAs: hi / lo split of the two plain tiles in shared memory =====
+      const int ct = (warp - 2) * 32 + lane;
+      for (int kb = 0; kb < nk; ++kb) {
+        const int st = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
+        mb_wait(&raw[st], ph);
+        unsigned char* base = smem + st * T2_STAGE_BYTES;
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {
+          uint4* x4 = reinterpret_cast<uint4*>(base + (op ? 2 * TC_A_BYTES : 0));
+          float4* l4 = reinterpret_cast<float4*>(base + (op ? 2 * TC_A_BYTES + T2_BHALF : TC_A_BYTES));
+#pragma unroll 4
+          for (int i = ct; i < TC_A_BYTES / 16; i += 64) {       // A tile and B half tile are both 16 KB
+            uint4 v = x4[i];
+            uint4 h = make_uint4(v.x & 0xffffe000u, v.y & 0xffffe000u, v.z & 0xffffe000u, v.w & 0xffffe000u);
+            l4[i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
+                                __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
+            x4[i] = h;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t fa;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(fa) : "r"(s_u32(&full[st])), "r"(0));
+          asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(fa) : "memory");
+        }
+      }
+    }
+  } else {
     // the "buffer drained" arrivals of both CTAs go to the leader's tempty barriers
     uint32_t te[2];
 #pragma unroll
@@ -568,8 +612,9 @@ static CUtensorMap make_map(const float* base, int rank, const cuuint64_t* dims,
   return m;
 }
 
-bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd) {
-  if (!L.W_hi || !x.split) return false;
+bool tc_conv_supported(ts_engine* e, const Layer& L, const Act3& x, int stride, int pd) {
+  const bool onchip = e->tc_pair && e->tc_onchip;     // plain operands, split on chip (CTA-pair kernel only)
+  if (onchip ? (!L.W || x.split) : (!L.W_hi || !x.split)) return false;
   if (x.C % TC_BK) return false;
   const int rows_in = x.T + 2 * x.pad + x.tail;
   if (rows_in % stride || (x.pad - pd) % stride || x.pad < pd) return false;
@@ -580,13 +625,14 @@ bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd) {
 void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
                cudaStream_t s, int y_tmul, int y_toff, int coff) {
   if (e->ws.sizing) return;
-  if (!tc_conv_supported(L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
+  if (!tc_conv_supported(e, L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
+  const bool onchip = e->tc_pair && e->tc_onchip;
   if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "tc_conv1d: layer/input mismatch");
   const int rows_in = x.T + 2 * x.pad + x.tail;
   const long R = (long)x.B * rows_in;
   const long Rs = R / stride;
   const float* base_hi = x.p;   // first padded row of batch 0 (Act3::p points at the allocation start)
-  const float* base_lo = x.lo;
+  const float* base_lo = onchip ? x.p : x.lo;
   cuuint64_t adims[3] = {(cuuint64_t)x.C, (cuuint64_t)stride, (cuuint64_t)Rs};
   cuuint64_t astr[2] = {(cuuint64_t)x.C * 4, (cuuint64_t)x.C * 4 * stride};
   // cluster shape: up to 4 N-tiles x 2 M-tiles share their operand boxes by TMA multicast
@@ -603,7 +649,7 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   cuuint64_t bdims[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
   cuuint64_t bstr[1] = {(cuuint64_t)L.K * 4};
   cuuint32_t bbox[2] = {TC_BK, (cuuint32_t)(TC_BN / cm)};   // pair: cm == 2 -> 128-row halves
-  CUtensorMap mBh = make_map(L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(L.W_lo, 2, bdims, bstr, bbox);
+  CUtensorMap mBh = make_map(onchip ? L.W : L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(onchip ? L.W : L.W_lo, 2, bdims, bstr, bbox);
   TcArgs P;
   P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
   P.rows_in = rows_in; P.off = x.pad - pd; P.T_out = T_out; P.nbatch = x.B; P.Rs = (int)Rs; P.N = L.N;
@@ -621,7 +667,8 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1') ? 1 : 0; }
   if (!e->tc_attr_set) {   // the max-dynamic-smem attribute is per device: cached per engine, not per process
     TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     e->tc_attr_set = true;
   }
   // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
@@ -637,7 +684,8 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   at[0].val.clusterDim.x = pair ? 2 : cn; at[0].val.clusterDim.y = pair ? 1 : cm; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel, mAh, mAl, mBh, mBl, P));
+  if (pair && onchip) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<true>, mAh, mAl, mBh, mBl, P));
+  else if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false>, mAh, mAl, mBh, mBl, P));
   else TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));
   e->launches++;
   TS_CUDA(cudaGetLastError());
@@ -653,7 +701,7 @@ void upload_weights(ts_engine* e, const std::vector<float>& W, Layer* L) {
 
 void conv_auto(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
                cudaStream_t s, int y_tmul, int y_toff, int coff) {
-  if (e->use_tc && (y.C % 4) == 0 && (coff % 4) == 0 && tc_conv_supported(L, x, stride, pd)) tc_conv1d(e, L, x, k, stride, pd, y, T_out, act, res, s, y_tmul, y_toff, coff);
+  if (e->use_tc && (y.C % 4) == 0 && (coff % 4) == 0 && tc_conv_supported(e, L, x, stride, pd)) tc_conv1d(e, L, x, k, stride, pd, y, T_out, act, res, s, y_tmul, y_toff, coff);
   else conv1d(e, L, x, k, stride, pd, y, T_out, act, res, s, y_tmul, y_toff, 0, coff);
 }
 
@@ -667,6 +715,7 @@ extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   e->tc_pair = enable == 1 || enable == 3;   // 1 (default) / 3 = CTA-pair (cta_group::2) 256x256 kernel
   e->tc_multicast = enable == 2;             // 2 = single-CTA 128x256 kernel in (n x 2) clusters with TMA multicast
                                              // 4 = single-CTA 128x256 kernel, no cluster
+  e->tc_onchip = enable == 1;                // 1 (default): plain operands split in shared memory; 3: operands pre-split in HBM
   return TS_OK;
 }
 
@@ -680,8 +729,19 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     p.A = A; p.W = W; p.bias = bias; p.C = C; p.M = M; p.N = N; p.K = K; p.mper = M; p.a_rs = K; p.kc = K; p.a_ts = K; p.c_rs = N; p.act = act; p.ldw = K;
     e->ws.sizing = false;
     launch_gemm(e, p, s);
+  } else if (mode == 2) {
+    if (K % TC_BK) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 32 for the tensor-core path");
+    if (!(e->tc_pair && e->tc_onchip)) fail(TS_ERR_INVALID, "ts_debug_gemm mode 2 needs ts_set_tensor_cores(e, 1)");
+    e->ws.sizing = false;
+    Layer L;
+    L.N = N; L.K = K; L.taps = 1; L.cin = K; L.W = const_cast<float*>(W); L.bias = const_cast<float*>(bias);
+    Act3 x; x.p = const_cast<float*>(A); x.split = false; x.B = 1; x.T = M; x.C = K; x.pad = 0;
+    Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
+    tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
   } else {
     if (K % TC_BK) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 32 for the tensor-core path");
+    const bool oc = e->tc_onchip;
+    e->tc_onchip = false;
     e->ws.sizing = false;
     float *ah, *al, *wh, *wl;
     TS_CUDA(cudaMalloc(&ah, (size_t)M * K * 4)); TS_CUDA(cudaMalloc(&al, (size_t)M * K * 4));
@@ -693,6 +753,7 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     Act3 x; x.p = ah; x.lo = al; x.split = true; x.B = 1; x.T = M; x.C = K; x.pad = 0;
     Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
     tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
+    e->tc_onchip = oc;
     TS_CUDA(cudaStreamSynchronize(s));
     cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
   }

@@ -69,7 +69,7 @@ void layernorm(ts_engine* e, const Act3& x, const float* g, const float* b, cons
                float eps, cudaStream_t s);
 
 // ---- tensor-core path (gemm_tc.cu): tcgen05 kind::tf32, 3xTF32 split, TMA-staged operands ------
-bool tc_conv_supported(const Layer& L, const Act3& x, int stride, int pd);
+bool tc_conv_supported(ts_engine* e, const Layer& L, const Act3& x, int stride, int pd);
 void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act,
                const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int coff = 0);
 void split_hi_lo(ts_engine* e, const float* x, float* hi, float* lo, long n, cudaStream_t s);
