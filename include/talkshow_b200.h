@@ -166,6 +166,7 @@ int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const 
 /* Dense-contraction kernel selection (default covered by the GPU tests; the others by scratch/ab_tc.py):
  * 1 (default) / 3: tcgen05 3xTF32 kernel, CTA pair (cta_group::2) 256x256 tile;
  * 4: tcgen05 3xTF32 kernel, single CTA 128x256 tile; 2: same in clusters with TMA multicast of the operand boxes;
+ * 5: CTA-pair kernel on plain operands, hi / lo split in shared memory by converter warps (bit-identical, measured slower);
  * 0: everything on the fp32 FFMA kernel. */
 int ts_set_tensor_cores(ts_engine* e, int enable);
 /* PixelCNN executor: 0 (default) = grid-wide persistent cooperative kernel (grid barrier; batch tile 16 / 32 / 64 picked per

@@ -4,6 +4,7 @@ import torch, ctypes as C
 from talkshow_b200 import _lib
 from talkshow_b200.engine import Engine
 e = Engine(0)
+e.set_tensor_cores(5)   # mode 2 of ts_debug_gemm = on-chip split; mode 1 always runs the pre-split kernel
 def run(mode, A, W, bias, act=0):
     M,K = A.shape; N = W.shape[0]
     out = torch.empty(M, N, device='cuda')

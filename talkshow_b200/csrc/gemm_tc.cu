@@ -398,11 +398,14 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on th
                : "memory");
 }
 
-// ONCHIP = true (round 2, default): the operands arrive as PLAIN fp32 — one TMA box per operand and k-block instead of two,
-// i.e. half the L2 -> shared-memory bytes that profiles/r01c identified as the limiter — and the two otherwise idle warps
+// ONCHIP = true (round 2 experiment, ts_set_tensor_cores(e, 5)): the operands arrive as PLAIN fp32 — one TMA box per operand
+// and k-block instead of two, i.e. half the L2 -> shared-memory bytes — and the two otherwise idle warps
 // of warpgroup 0 split them in shared memory: lo = x - (x & 0xffffe000) is written to the `lo` tile at the SAME offset
-// (elementwise, so the 128 B swizzle is irrelevant), x itself is truncated in place to the `hi` value.  The converters of
-// both CTAs then arrive on the leader's `full` barrier (generic -> async proxy fence first), which the MMA issuer waits on.
+// (elementwise, so the 128 B swizzle is irrelevant); x itself serves as the `hi` operand — measured: kind::tf32 ignores the
+// 13 low mantissa bits, results are bit-identical to the pre-split kernel.  The converters of both CTAs then arrive on the
+// leader's `full` barrier (generic -> async proxy fence first), which the MMA issuer waits on.  Measured (face, 64 clips x
+// 10 s): 66.5 ms vs 54.1 ms with operands pre-split in HBM — the extra hop (TMA -> converter -> MMA) on a 3-stage ring costs
+// more than the halved L2 -> SM traffic gains, so pre-split stays the default (profiles/r02_summary.md).
 template <bool ONCHIP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
@@ -529,7 +532,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
             uint4 h = make_uint4(v.x & 0xffffe000u, v.y & 0xffffe000u, v.z & 0xffffe000u, v.w & 0xffffe000u);
             l4[i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
                                 __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
-            x4[i] = h;
+            if (P.nprod == 4) x4[i] = h;   // TS_TC_NPROD=4: also truncate x in place (the tensor core ignores the 13 low bits itself)
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
@@ -661,7 +664,7 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.r_bs = res ? res->bstride() : 0; P.r_rs = res ? res->C : 0;
   P.act = act;
   P.cn = pair ? tiles_n : cn; P.cm = cm;
-  { const char* np = getenv("TS_TC_NPROD"); P.nprod = (np && np[0] == '1') ? 1 : 3; }
+  { const char* np = getenv("TS_TC_NPROD"); P.nprod = (np && np[0] == '1') ? 1 : (np && np[0] == '4') ? 4 : 3; }
   P.a_hi = base_hi; P.a_lo = base_lo; P.a_rows = R;
   // whole-row L2 prefetch measured slower (96 vs 89 ms per face pass): off unless TS_TC_ROWPF=1
   { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1') ? 1 : 0; }
@@ -712,10 +715,10 @@ using namespace ts;
 extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   if (!e) return TS_ERR_INVALID;
   e->use_tc = enable != 0;
-  e->tc_pair = enable == 1 || enable == 3;   // 1 (default) / 3 = CTA-pair (cta_group::2) 256x256 kernel
+  e->tc_pair = enable == 1 || enable == 3 || enable == 5;   // 1 (default) / 3 = CTA-pair (cta_group::2) 256x256 kernel
   e->tc_multicast = enable == 2;             // 2 = single-CTA 128x256 kernel in (n x 2) clusters with TMA multicast
                                              // 4 = single-CTA 128x256 kernel, no cluster
-  e->tc_onchip = enable == 1;                // 1 (default): plain operands split in shared memory; 3: operands pre-split in HBM
+  e->tc_onchip = enable == 5;                // 5 = CTA-pair kernel on PLAIN operands, hi / lo split in shared memory (experiment)
   return TS_OK;
 }
 
@@ -731,7 +734,7 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     launch_gemm(e, p, s);
   } else if (mode == 2) {
     if (K % TC_BK) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 32 for the tensor-core path");
-    if (!(e->tc_pair && e->tc_onchip)) fail(TS_ERR_INVALID, "ts_debug_gemm mode 2 needs ts_set_tensor_cores(e, 1)");
+    if (!(e->tc_pair && e->tc_onchip)) fail(TS_ERR_INVALID, "ts_debug_gemm mode 2 needs ts_set_tensor_cores(e, 5)");
     e->ws.sizing = false;
     Layer L;
     L.N = N; L.K = K; L.taps = 1; L.cin = K; L.W = const_cast<float*>(W); L.bias = const_cast<float*>(bias);
