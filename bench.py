@@ -32,6 +32,9 @@ import torch  # noqa: E402
 FPS = 30
 METRIC = "smplx_motion_frames_per_sec"
 CPU_THREADS = 32     # thread count of the CPU arm (see cpu_threads())
+# DRAM bytes per latent row of the persistent PixelCNN kernel by batch tile, from `ncu --set full` captures of the kernel alone
+# (profiles/r02_pixelcnn_ncu_summary.md); the algorithmic figure is 89.8 MB per row
+NCU_DRAM_BYTES_PER_ROW = {64: 163.6e6, 32: 158.0e6, 16: 153.0e6}
 
 
 def env_int(k, d):
@@ -360,8 +363,9 @@ def run_ours(args, rank, world, local_rank):
                           "%d samples on this GPU)" % (tile, T, main.b),
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "traffic": None, "traffic_source": "ncu dram__bytes_read+write of this kernel: profiles/ (163.8 MB/row at the 64-sample tile); "
-                "staged bytes per launch: %d" % (eng.pixelcnn_staged_row_bytes * T), "launch_ms": pix_avg,
+                "traffic": NCU_DRAM_BYTES_PER_ROW[tile] * T, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this "
+                "kernel per latent row (profiles/r02_pixelcnn_ncu_summary.md: 163.6 MB at the 64-sample tile, 153.0 MB at the 16-sample tile; 32: "
+                "between, not captured) x %d rows; staged bytes per launch: %d" % (T, eng.pixelcnn_staged_row_bytes * T), "launch_ms": pix_avg,
                 "algorithmic_bytes": alg_bytes, "share_of_step": pix_avg / (dev_ms / args.steps)}
     # 106 GFLOP per 10 s clip (53 GMAC), scaled with the clip length
     face_flop = 106.0e9 * main.b * args.seconds / 10.0

@@ -309,7 +309,7 @@ def test_device_mfcc_matches_torchaudio(eng):
         assert got.shape == ref.shape, (got.shape, ref.shape)
         err = np.abs(got - ref).max()
         print("device MFCC vs torchaudio (sr0=%d): max-abs %.3e (|ref| max %.1f)" % (sr0, err, np.abs(ref).max()))
-        assert err <= 2e-2
+        assert err <= 1e-3          # measured 2e-4 (fp32 DFT / mel / DCT as GEMMs vs torchaudio's FFT chain, |ref| up to ~600 dB-scaled units)
 
 
 def test_rot6d_to_axis_angle(eng):

@@ -11,12 +11,10 @@ from talkshow_b200 import _lib, synth
 from talkshow_b200.engine import Engine
 
 
-@pytest.fixture(scope="module", params=["fused", "plain", "cluster", "sched2"])
+@pytest.fixture(scope="module", params=["fused", "plain", "sched2"])
 def plan(ckpts, request):
     e = Engine(-148)            # host-only planning engine sized for 148 SMs
     e.set_pixelcnn_fusion({"plain": 0, "sched2": 2}.get(request.param, 1))
-    if request.param == "cluster":
-        e.set_pixelcnn_mode(3)  # experimental cluster plan: 33 clusters x 4 CTAs, K split inside the cluster
     e.load_pixelcnn(ckpts["pixel"]["generator"])
     table, blob = _lib.plan_to_numpy(e.h)
     rb = e.pixelcnn_row_bytes
