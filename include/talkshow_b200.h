@@ -184,6 +184,11 @@ int ts_pixelcnn_plan_shape(ts_engine* e, int* nstages, int* ncta);
 int ts_pixelcnn_trace(ts_engine* e, int row);
 int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len);
 
+/* Persistent CTAs of the grid-wide plan built by the NEXT ts_load_pixelcnn (0 = one per SM).  A smaller even count (>= 64)
+ * launches the sampler as CTA pairs on that many SMs and leaves the other TPCs free for kernels of another stream: with
+ * 8 clips per GPU the latency-bound sampler and the face regressor run side by side (talkshow_b200/pipeline.py). */
+int ts_set_pixelcnn_ctas(ts_engine* e, int n);
+
 /* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
  * stack multiplied together at load, layer-0 gate of column 1 gathered from a code table), 0 = plain 84-stage plan
  * (one stage per reference conv), 2 = EXPERIMENTAL: the fused plan with vert_to_horiz taken out of the vertical stages

@@ -13,10 +13,10 @@ def run(mode, A, W, bias, act=0):
     torch.cuda.synchronize()
     return out
 torch.manual_seed(0)
-for (M,N,K) in [(128,128,32),(128,128,64),(300,200,96),(4096,512,1536),(1000,64,512),(777,3072,768)]:
+for (M,N,K) in [(128,128,64),(300,200,192),(4096,512,1536),(1000,64,512),(777,3072,768),(19200,768,3072)]:
     A = torch.randn(M,K,device='cuda'); W = torch.randn(N,K,device='cuda')/K**0.5; b = torch.randn(N,device='cuda')
     ref = (A.double() @ W.double().t() + b.double())
-    for mode in (0,1,2):
+    for mode in (0,1,2,3):
         try:
             out = run(mode, A, W, b)
             err = (out.double()-ref).abs().max().item()
@@ -26,7 +26,7 @@ for (M,N,K) in [(128,128,32),(128,128,64),(300,200,96),(4096,512,1536),(1000,64,
 # timing
 M,N,K = 65536, 768, 3072
 A = torch.randn(M,K,device='cuda'); W = torch.randn(N,K,device='cuda')/K**0.5; b = torch.zeros(N,device='cuda')
-for mode in (0,1,2):
+for mode in (0,1,2,3):
     out = run(mode, A, W, b)
     t0=torch.cuda.Event(enable_timing=True); t1=torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); t0.record(); out = run(mode, A, W, b); t1.record(); torch.cuda.synchronize()

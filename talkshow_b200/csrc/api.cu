@@ -12,6 +12,12 @@ float* ts_engine::upload(const std::vector<float>& h) {
   TS_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
   return (float*)d;
 }
+unsigned short* ts_engine::upload(const std::vector<unsigned short>& h) {
+  if (host_only) return nullptr;
+  void* d = dmalloc(h.size() * sizeof(unsigned short));
+  TS_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  return (unsigned short*)d;
+}
 void* ts_engine::dmalloc(size_t bytes) {
   if (host_only) return nullptr;
   void* d = nullptr;
@@ -72,6 +78,12 @@ extern "C" int64_t ts_launch_count(ts_engine* e) { return e ? e->launches : 0; }
 extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
   if (!e || mode < 0 || mode > 2) return TS_ERR_INVALID;
   e->pixel_mode = mode;
+  return TS_OK;
+}
+
+extern "C" int ts_set_pixelcnn_ctas(ts_engine* e, int n) {
+  if (!e || n < 0) return TS_ERR_INVALID;
+  e->pixel_ctas = n;
   return TS_OK;
 }
 

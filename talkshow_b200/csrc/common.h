@@ -111,6 +111,9 @@ struct Layer {
   float* W = nullptr;
   float* W_hi = nullptr;  // 3xTF32 split copies for the tensor-core path (gemm_tc.cu), optional
   float* W_lo = nullptr;
+  unsigned short* W_h16 = nullptr;   // fp16-split copies of W * 2^w_shift (power-of-two scale keeps the low plane normal)
+  unsigned short* W_l16 = nullptr;
+  float w_unscale = 1.f;             // 2^-w_shift, applied to the accumulator in the epilogue (exact)
   float* bias = nullptr;
   int N = 0, K = 0, taps = 1, cin = 0;  // cin = padded input channels
 };
@@ -128,9 +131,11 @@ struct ts_engine {
   std::string err;
   int64_t launches = 0;
   int pixel_mode = 0;
+  int pixel_ctas = 0;        // > 0: persistent CTAs of the grid-wide PixelCNN plan built at the next load (default: one per SM)
   int pixel_fusion = 1;      // plan built at ts_load_pixelcnn: 0 plain 84-stage, 1 fused 52-stage, 2 fused + vert_to_horiz in the horizontal pass
   bool tc_pair = true;       // CTA-pair (cta_group::2) 256x256 tensor-core kernel (default)
   bool tc_onchip = false;    // experiment (mode 5): CTA-pair kernel takes plain fp32 operands and splits them hi / lo in shared memory
+  bool tc_f16 = false;       // CTA-pair kernel on fp16-split operands (kind::f16, 3 products at twice the tf32 rate)
   bool tc_multicast = false;  // share operand boxes inside a thread-block cluster by TMA multicast
   bool tc_attr_set = false;  // cudaFuncSetAttribute(max dynamic smem) of the tcgen05 kernels done on this engine's device
   bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows
@@ -147,6 +152,7 @@ struct ts_engine {
   std::map<std::string, std::vector<void*>> slot_mem;
   std::vector<void*>* alloc_sink = nullptr;
   float* upload(const std::vector<float>& h);
+  unsigned short* upload(const std::vector<unsigned short>& h);
   void* dmalloc(size_t bytes);
 };
 

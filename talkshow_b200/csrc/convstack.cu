@@ -174,7 +174,12 @@ Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool sp
   a.tail = tail;
   a.split = split;
   a.p = e->ws.alloc<float>(a.numel());
-  if (split) a.lo = e->ws.alloc<float>(a.numel());
+  if (split && e->tc_f16) {
+    a.h16 = e->ws.alloc<unsigned short>(a.numel());
+    a.l16 = e->ws.alloc<unsigned short>(a.numel());
+  } else if (split) {
+    a.lo = e->ws.alloc<float>(a.numel());
+  }
   zero_pads(e, a, s);
   return a;
 }

@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
       for (int j = 0; j < 10; ++j) y = fmaf(wr[j], xs[t * 5 + j], y);
       float v = (y - mu) * rstd * gg + bb;
       v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-      if (out.lo) {
+      if (out.h16) {
+        out.row(b, t0 + t)[c] = v;
+        split16(v, out.row_h16(b, t0 + t)[c], out.row_l16(b, t0 + t)[c]);
+      } else if (out.lo) {
         float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         out.row(b, t0 + t)[c] = h;
         out.row_lo(b, t0 + t)[c] = v - h;
@@ -185,7 +188,10 @@ __global__ void ln_pre_kernel(Act3 x, Act3 pre, int has_pre, const float* __rest
     float o = (v[n] - mean) * rstd * g[c] + bta[c];
     if (rr) o += rl ? (rr[c] + rl[c]) : rr[c];
     if (act == ACT_RELU) o = o > 0.f ? o : 0.f;
-    if (yl) {
+    if (y.h16) {
+      yr[c] = o;
+      split16(o, y.row_h16(b, t)[c], y.row_l16(b, t)[c]);
+    } else if (yl) {
       float h = __uint_as_float(__float_as_uint(o) & 0xffffe000u);
       yr[c] = h;
       yl[c] = o - h;
@@ -659,7 +665,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16_kernel(cons
 // loops are 4 LDS + 3 HMMA per product triple.  Same bytes of shared memory as the fp32 copies.
 constexpr int ATT_KW = 36;    // K plane row stride in 32-bit words (72 halves): fragment loads conflict-free
 __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16p_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                                             float* __restrict__ out_lo, int T, int H, float scale) {
+                                                                             float* __restrict__ out_lo, unsigned short* __restrict__ o_h16,
+                                                                             unsigned short* __restrict__ o_l16, int T, int H, float scale) {
   extern __shared__ __align__(16) uint32_t smw[];
   const int Tp = (T + 63) & ~63;
   const int VW = Tp / 2 + 4;                       // V^T plane row stride in words (Tp halves + 8 pad)
@@ -803,7 +810,13 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16p_kernel(con
         const float inv = half ? ib : ia;
         const float v0 = o[dt][half * 2] * inv, v1 = o[dt][half * 2 + 1] * inv;
         const size_t at = ((size_t)b * T + row) * (H * 64) + h * 64 + dt * 8 + 2 * t;
-        if (out_lo) {
+        if (o_h16) {   // fp16-split copy for the out_proj GEMM; `out` keeps the full value
+          *reinterpret_cast<float2*>(out + at) = make_float2(v0, v1);
+          uint32_t hh, ll;
+          split_h2(v0, v1, hh, ll);
+          *reinterpret_cast<uint32_t*>(o_h16 + at) = hh;
+          *reinterpret_cast<uint32_t*>(o_l16 + at) = ll;
+        } else if (out_lo) {
           const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
           *reinterpret_cast<float2*>(out + at) = make_float2(h0, h1);
           *reinterpret_cast<float2*>(out_lo + at) = make_float2(v0 - h0, v1 - h1);
@@ -820,7 +833,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16p_kernel(con
 // (clip x head, query tiles of 16 x ATT_WARPS rows).  No limit on the clip length (the resident variant above needs the
 // whole sequence in shared memory: <= 384 frames = 12.8 s).
 __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                                             float* __restrict__ out_lo, int T, int H, float scale, int CH) {
+                                                                             float* __restrict__ out_lo, unsigned short* __restrict__ o_h16,
+                                                                             unsigned short* __restrict__ o_l16, int T, int H, float scale, int CH) {
   extern __shared__ __align__(16) uint32_t smw[];
   const int Tp = CH;                               // keys resident per chunk (multiple of 64)
   const int VW = Tp / 2 + 4;                       // V^T plane row stride in words (Tp halves + 8 pad)
@@ -976,7 +990,13 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
         const float inv = half ? ib : ia;
         const float v0 = o[dt][half * 2] * inv, v1 = o[dt][half * 2 + 1] * inv;
         const size_t at = ((size_t)b * T + row) * (H * 64) + h * 64 + dt * 8 + 2 * t;
-        if (out_lo) {
+        if (o_h16) {   // fp16-split copy for the out_proj GEMM; `out` keeps the full value
+          *reinterpret_cast<float2*>(out + at) = make_float2(v0, v1);
+          uint32_t hh, ll;
+          split_h2(v0, v1, hh, ll);
+          *reinterpret_cast<uint32_t*>(o_h16 + at) = hh;
+          *reinterpret_cast<uint32_t*>(o_l16 + at) = ll;
+        } else if (out_lo) {
           const float h0 = __uint_as_float(__float_as_uint(v0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(v1) & 0xffffe000u);
           *reinterpret_cast<float2*>(out + at) = make_float2(h0, h1);
           *reinterpret_cast<float2*>(out_lo + at) = make_float2(v0 - h0, v1 - h1);
@@ -989,15 +1009,17 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
 }
 
 
-static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo, int B, int T, int H, cudaStream_t s) {
+static void attention(ts_engine* e, const float* qkv, const Act3& o, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
+  float* out = o.p;
+  float* out_lo = o.lo;
   static const int att_mode = getenv("TS_ATT_MMA") ? atoi(getenv("TS_ATT_MMA")) : 3;   // A/B switch: 0 FFMA, 1 tf32 MMA, 2 fp16-split MMA, 3 fp16-split MMA with K/V split once per CTA
   if (att_mode == 3) {
     const int Tp64 = (T + 63) & ~63;
     const size_t smem16p = ((size_t)2 * Tp64 * ATT_KW + (size_t)2 * 64 * (Tp64 / 2 + 4)) * sizeof(uint32_t);
     if (smem16p <= 220 * 1024) {
       TS_CUDA(cudaFuncSetAttribute(attention_mma16p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16p));
-      attention_mma16p_kernel<<<B * H, ATT_WARPS * 32, smem16p, s>>>(qkv, out, out_lo, T, H, 0.125f);
+      attention_mma16p_kernel<<<B * H, ATT_WARPS * 32, smem16p, s>>>(qkv, out, out_lo, o.h16, o.l16, T, H, 0.125f);
       e->launches++;
       TS_CUDA(cudaGetLastError());
       return;
@@ -1007,11 +1029,12 @@ static void attention(ts_engine* e, const float* qkv, float* out, float* out_lo,
     const size_t smem16t = ((size_t)2 * CH * ATT_KW + (size_t)2 * 64 * (CH / 2 + 4)) * sizeof(uint32_t);
     TS_CUDA(cudaFuncSetAttribute(attention_mma16t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16t));
     const int nrb = (T + 15) / 16;
-    attention_mma16t_kernel<<<dim3(B * H, cdiv(nrb, ATT_WARPS)), ATT_WARPS * 32, smem16t, s>>>(qkv, out, out_lo, T, H, 0.125f, CH);
+    attention_mma16t_kernel<<<dim3(B * H, cdiv(nrb, ATT_WARPS)), ATT_WARPS * 32, smem16t, s>>>(qkv, out, out_lo, o.h16, o.l16, T, H, 0.125f, CH);
     e->launches++;
     TS_CUDA(cudaGetLastError());
     return;
   }
+  if (o.h16) fail(TS_ERR_UNSUPPORTED, "attention: TS_ATT_MMA=%d has no fp16-split output (use the default, or ts_set_tensor_cores(e, 1))", att_mode);
   if (att_mode == 2 || att_mode == 3) {
     const int Tp64 = (T + 63) & ~63;
     const size_t smem16 = (size_t)Tp64 * (ATT_LDK + ATT_LDV) * sizeof(float);
@@ -1114,7 +1137,7 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   Act3 ff = new_act(e, B, frame, 3072, 0, s, tc);
   for (auto& L : F.layers) {
     linear(e, L.qkv, hcur, qkv, ACT_NONE, nullptr, s);
-    attention(e, qkv.p, att.p, att.lo, B, frame, 12, s);
+    attention(e, qkv.p, att, B, frame, 12, s);
     linear(e, L.out, att, t1, ACT_NONE, &hcur, s);                       // h + out_proj(attn)
     ln_pre(e, t1, nullptr, L.ln1_g, L.ln1_b, hcur, nullptr, ACT_NONE, s);
     linear(e, L.ff1, hcur, ff, ACT_GELU, nullptr, s);

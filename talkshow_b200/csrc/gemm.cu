@@ -139,6 +139,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
   const float* bias = p.bias ? p.bias + g * p.n_goff : nullptr;
   float* C = p.C + g * p.n_goff;
   float* C_lo = p.C_lo ? p.C_lo + g * p.n_goff : nullptr;
+  unsigned short* C_h16 = p.C_h16 ? p.C_h16 + g * p.n_goff : nullptr;
+  unsigned short* C_l16 = p.C_l16 ? p.C_l16 + g * p.n_goff : nullptr;
   const float* R = p.R ? p.R + g * p.n_goff : nullptr;
   const float* R_lo = p.R_lo ? p.R_lo + g * p.n_goff : nullptr;
   const bool vec = ((p.c_rs | p.c_bs | p.r_rs | p.r_bs | p.n_goff) & 3) == 0 && (p.N & 3) == 0 &&
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
     int b = m / p.mper, t = m - b * p.mper;
     float* crow = C + b * p.c_bs + t * p.c_rs;
     float* crow_lo = C_lo ? C_lo + b * p.c_bs + t * p.c_rs : nullptr;
+    unsigned short* crow_h16 = C_h16 ? C_h16 + b * p.c_bs + t * p.c_rs : nullptr;
+    unsigned short* crow_l16 = C_h16 ? C_l16 + b * p.c_bs + t * p.c_rs : nullptr;
     const float* rrow = R ? R + b * p.r_bs + t * p.r_rs : nullptr;
     const float* rrow_lo = R_lo ? R_lo + b * p.r_bs + t * p.r_rs : nullptr;
 #pragma unroll
@@ -170,7 +174,14 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN), 2) gemm_kernel(GemmP p)
         }
         v[q] = x;
       }
-      if (crow_lo) {
+      if (crow_h16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (n + q < p.N) {
+            crow[n + q] = v[q];
+            split16(v[q], crow_h16[n + q], crow_l16[n + q]);
+          }
+      } else if (crow_lo) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (n + q < p.N) {
@@ -215,6 +226,7 @@ void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int 
   p.A = x.row(0, 0) + (long)(x_toff - pd) * x.C;
   if (x.lo) p.A_lo = x.row_lo(0, 0) + (long)(x_toff - pd) * x.C;
   if (y.lo) p.C_lo = y.row_lo(0, y_toff) + coff;
+  if (y.h16) { p.C_h16 = y.row_h16(0, y_toff) + coff; p.C_l16 = y.row_l16(0, y_toff) + coff; }
   p.W = L.W;
   p.bias = L.bias;
   p.C = y.row(0, y_toff) + coff;
@@ -296,6 +308,7 @@ __global__ void zero_pads_kernel(Act3 a) {
     int t = row < a.pad ? row - a.pad : a.T + (row - a.pad);
     a.row(b, t)[c] = 0.f;
     if (a.lo) a.row_lo(b, t)[c] = 0.f;
+    if (a.h16) { a.row_h16(b, t)[c] = 0; a.row_l16(b, t)[c] = 0; }
   }
 }
 

@@ -12,7 +12,16 @@
 //  A Conv1d(k, stride s) is the same kernel: the A tensor map is 3-D {C, s, rows/s} over the padded
 //  channel-last buffer, tap t reads box (c0, t % s, j + t / s); GEMM rows are indexed by the padded row
 //  index j, rows that fall on padding are computed and discarded by the epilogue.
+//
+// fp16-split variant (ts_set_tensor_cores(e, 6), the default): the same two-term split carried by fp16 instead of tf32 —
+// x = h + l with h = fp16(x), l = fp16(x - h): 11 + 11 significant bits, the same as two tf32 terms — and the three
+// products issued as kind::f16, which runs at twice the tf32 rate: a k-block of 128 bytes per row holds 64 K values
+// instead of 32, so the same 12 MMAs per stage cover twice the K.  Half the tensor time, half the operand bytes
+// (HBM, L2 -> shared memory and shared memory -> tensor core).  Range: |x| < 65504 (fp16); weights are pre-scaled by a
+// power of two per layer so their low plane stays normal (undone exactly in the epilogue); activations whose low plane
+// underflows lose absolute accuracy below 2^-25 only.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "kernels.h"
 
@@ -54,6 +63,10 @@ struct TcArgs {
   int nprod;                        // 3 (normal) or 1 (hi*hi only: throughput experiment)
   int prefetch_rows;                // pair kernel: whole-row L2 prefetch of the A operand one tap ahead
   int cn, cm;                       // cluster shape: cn N-tiles x cm M-tiles share operands by TMA multicast
+  int chunk;                        // k-blocks accumulated in TMEM before the epilogue drains them (K = 256)
+  float oscale;                     // accumulator scale (undoes the power-of-two weight scale of the fp16 split), 1 for tf32
+  unsigned short* c_h16;            // fp16-split copy of the output (c_hi then holds the full value, c_lo is null)
+  unsigned short* c_l16;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,7 +185,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem
   float acc[EC];
 #pragma unroll
   for (int i = 0; i < EC; ++i) acc[i] = 0.f;
-  const int nchunks = (nk + TC_CHUNK - 1) / TC_CHUNK;
+  const int nchunks = (nk + P.chunk - 1) / P.chunk;
   for (int c = 0; c < nchunks; ++c) {
     const int buf = c & 1;
     mb_wait(&tfull[buf], (c >> 1) & 1);
@@ -225,13 +238,23 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (n + q < P.N) {
-        float x = o[q];
+        float x = o[q] * P.oscale;
         if (P.bias) x += P.bias[n + q];
         if (P.r_hi) x += P.r_lo ? (P.r_hi[roff + q] + P.r_lo[roff + q]) : P.r_hi[roff + q];
         o[q] = tc_act(x, P.act);
       }
     }
-    if (n + 3 < P.N) {
+    if (P.c_h16) {
+      for (int q = 0; q < 4 && n + q < P.N; ++q) P.c_hi[coff + q] = o[q];
+      if (n + 3 < P.N) {
+        ushort4 h, l;
+        split16(o[0], h.x, l.x); split16(o[1], h.y, l.y); split16(o[2], h.z, l.z); split16(o[3], h.w, l.w);
+        *reinterpret_cast<ushort4*>(P.c_h16 + coff) = h;
+        *reinterpret_cast<ushort4*>(P.c_l16 + coff) = l;
+      } else {
+        for (int q = 0; q < 4 && n + q < P.N; ++q) split16(o[q], P.c_h16[coff + q], P.c_l16[coff + q]);
+      }
+    } else if (n + 3 < P.N) {
       if (P.c_lo) {
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
@@ -325,7 +348,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % TC_STAGES, ph = (kb / TC_STAGES) & 1;
-        const int chunk = kb / TC_CHUNK, kin = kb - chunk * TC_CHUNK, buf = chunk & 1;
+        const int chunk = kb / P.chunk, kin = kb - chunk * P.chunk, buf = chunk & 1;
         if (kin == 0) {                       // this accumulator buffer must have been drained
           mb_wait(&tempty[buf], ((chunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -347,7 +370,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant_
           }
         }
         umma_commit_mc(&empty[st], mask_row | mask_col);   // release the stage to every CTA that filled it
-        if (kin == TC_CHUNK - 1 || kb == nk - 1) umma_commit(&tfull[buf]);   // chunk accumulated
+        if (kin == P.chunk - 1 || kb == nk - 1) umma_commit(&tfull[buf]);   // chunk accumulated
       }
     }
   } else if (warp >= 4) {
@@ -392,6 +415,12 @@ __device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a, uint64_t
       "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem), "l"(a), "l"(b),
+      "r"(idesc), "r"(accum)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s_u32(bar)),
                "h"((uint16_t)3)
@@ -406,7 +435,8 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {   // arrives on th
 // leader's `full` barrier (generic -> async proxy fence first), which the MMA issuer waits on.  Measured (face, 64 clips x
 // 10 s): 66.5 ms vs 54.1 ms with operands pre-split in HBM — the extra hop (TMA -> converter -> MMA) on a 3-stage ring costs
 // more than the halved L2 -> SM traffic gains, so pre-split stays the default (profiles/r02_summary.md).
-template <bool ONCHIP>
+// F16 = true: operands are fp16 planes (h16, l16), k-blocks of 64 K values, kind::f16 (see the file header).
+template <bool ONCHIP, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
                 const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P) {
@@ -425,6 +455,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
   const int lin = blockIdx.x >> 1, nt = lin % P.cn, mp = lin / P.cn;
   const int j0 = (2 * mp + (int)rank) * TC_BM, n0 = nt * TC_BN;
   const int nk = P.taps * P.cblocks;
+  constexpr int BK = F16 ? 2 * TC_BK : TC_BK;      // K values per 128-byte k-block row
+  static_assert(!(ONCHIP && F16), "the on-chip split experiment exists for tf32 operands only");
 
   if (threadIdx.x == 0) {
     // full: TMA bytes of both CTAs (pre-split operands) or the 2 x 2 converter warps of the pair (ONCHIP)
@@ -452,7 +484,7 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
     // tap ahead, so DRAM sees 2-4 KB bursts instead of the 128-byte pieces the k-block boxes would request
     auto prefetch_tap = [&](int tap) {
       if (tap >= P.taps) return;
-      const uint32_t bytes = (uint32_t)P.C * 4u;
+      const uint32_t bytes = (uint32_t)P.C * 4u;   // tf32 operands only (P.prefetch_rows is 0 for fp16 planes)
       for (int r = lane; r < TC_BM; r += 32) {
         const long row = (long)(j0 + r + tap / P.stride) * P.stride + tap % P.stride;
         if (row < P.a_rows) {
@@ -472,8 +504,8 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
         mb_wait(&empty[st], ph ^ 1);
         const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
         unsigned char* base = smem + st * T2_STAGE_BYTES;
-        const int c0 = cb * TC_BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
-        const int kcol = tap * P.C + cb * TC_BK, nrow = n0 + (int)rank * (TC_BN / 2);
+        const int c0 = cb * BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
+        const int kcol = tap * P.C + cb * BK, nrow = n0 + (int)rank * (TC_BN / 2);
         if constexpr (ONCHIP) {
           mb_expect(&raw[st], TC_A_BYTES + T2_BHALF);                       // this CTA's two plain boxes, on its own barrier
           tma_3d(base, &mA_hi, c0, c1, c2, &raw[st]);
@@ -491,10 +523,12 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {  // ===== MMA issuer: leader CTA only =====
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      // instruction descriptor: D = F32 (bit 4), A / B format (bits 7.., 10..) TF32 = 2 or F16 = 0, N >> 3 at 17, M >> 4 at 24
+      const uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
       for (int kb = 0; kb < nk; ++kb) {
         const int st = kb % T2_STAGES, ph = (kb / T2_STAGES) & 1;
-        const int chunk = kb / TC_CHUNK, kin = kb - chunk * TC_CHUNK, buf = chunk & 1;
+        const int chunk = kb / P.chunk, kin = kb - chunk * P.chunk, buf = chunk & 1;
         if (kin == 0) {
           mb_wait(&tempty[buf], ((chunk >> 1) & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -505,13 +539,19 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
         const uint32_t d = tmem_base + buf * TC_BN;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint32_t o = k * 32;
-          umma2_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
-          umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
-          umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          const uint32_t o = k * 32;    // 32 bytes along K inside the 128 B swizzle atom: 8 tf32 or 16 fp16 = one MMA's K
+          if constexpr (F16) {
+            umma2_f16(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+            umma2_f16(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+            umma2_f16(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          } else {
+            umma2_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+            umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+            umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+          }
         }
         umma2_commit(&empty[st]);
-        if (kin == TC_CHUNK - 1 || kb == nk - 1) umma2_commit(&tfull[buf]);
+        if (kin == P.chunk - 1 || kb == nk - 1) umma2_commit(&tfull[buf]);
       }
     }
   } else if (warp < 4) {
@@ -576,6 +616,31 @@ void split_hi_lo(ts_engine* e, const float* x, float* hi, float* lo, long n, cud
   e->launches++;
   TS_CUDA(cudaGetLastError());
 }
+__global__ void split16_kernel(const float* __restrict__ x, unsigned short* __restrict__ h, unsigned short* __restrict__ l, long n, float scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) split16(x[i] * scale, h[i], l[i]);
+}
+// fp16 planes of W * 2^shift; the shift puts max|W| just below 2^14 (clamped to [0, 14]) and comes back as 2^-shift
+static float split16_host(const std::vector<float>& w, std::vector<unsigned short>* h, std::vector<unsigned short>* l) {
+  float mx = 0.f;
+  for (float v : w) mx = std::max(mx, std::fabs(v));
+  int shift = 0;
+  if (mx > 0.f && std::isfinite(mx)) {
+    int ex;
+    std::frexp(mx, &ex);            // mx = m * 2^ex, m in [0.5, 1)
+    shift = std::min(14, std::max(0, 14 - ex));
+  }
+  const float sc = std::ldexp(1.0f, shift);
+  h->resize(w.size());
+  l->resize(w.size());
+  for (size_t i = 0; i < w.size(); ++i) {
+    const float v = w[i] * sc;
+    const __half hh = __float2half_rn(v);
+    const __half ll = __float2half_rn(v - __half2float(hh));
+    (*h)[i] = __half_as_ushort(hh);
+    (*l)[i] = __half_as_ushort(ll);
+  }
+  return std::ldexp(1.0f, -shift);
+}
 void split_host(const std::vector<float>& w, std::vector<float>* hi, std::vector<float>* lo) {
   hi->resize(w.size());
   lo->resize(w.size());
@@ -605,10 +670,11 @@ static EncodeTiledFn get_encode() {
   }
   return fn;
 }
-static CUtensorMap make_map(const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+static CUtensorMap make_map(const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                            bool f16 = false) {
   CUtensorMap m;
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = get_encode()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) fail(TS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu", (int)r, rank, (unsigned long long)dims[0],
                               (unsigned long long)dims[1]);
@@ -617,8 +683,13 @@ static CUtensorMap make_map(const float* base, int rank, const cuuint64_t* dims,
 
 bool tc_conv_supported(ts_engine* e, const Layer& L, const Act3& x, int stride, int pd) {
   const bool onchip = e->tc_pair && e->tc_onchip;     // plain operands, split on chip (CTA-pair kernel only)
-  if (onchip ? (!L.W || x.split) : (!L.W_hi || !x.split)) return false;
-  if (x.C % TC_BK) return false;
+  const bool f16 = e->tc_pair && e->tc_f16;           // fp16 planes
+  if (f16) {
+    if (!L.W_h16 || !x.h16 || x.C % (2 * TC_BK)) return false;
+  } else {
+    if (onchip ? (!L.W || x.split) : (!L.W_hi || !x.lo)) return false;
+    if (x.C % TC_BK) return false;
+  }
   const int rows_in = x.T + 2 * x.pad + x.tail;
   if (rows_in % stride || (x.pad - pd) % stride || x.pad < pd) return false;
   return true;
@@ -630,14 +701,16 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   if (e->ws.sizing) return;
   if (!tc_conv_supported(e, L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
   const bool onchip = e->tc_pair && e->tc_onchip;
+  const bool f16 = e->tc_pair && e->tc_f16;
+  const int esz = f16 ? 2 : 4, bk = f16 ? 2 * TC_BK : TC_BK;
   if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "tc_conv1d: layer/input mismatch");
   const int rows_in = x.T + 2 * x.pad + x.tail;
   const long R = (long)x.B * rows_in;
   const long Rs = R / stride;
-  const float* base_hi = x.p;   // first padded row of batch 0 (Act3::p points at the allocation start)
-  const float* base_lo = onchip ? x.p : x.lo;
+  const void* base_hi = f16 ? (const void*)x.h16 : (const void*)x.p;   // first padded row of batch 0 (allocation start)
+  const void* base_lo = f16 ? (const void*)x.l16 : onchip ? (const void*)x.p : (const void*)x.lo;
   cuuint64_t adims[3] = {(cuuint64_t)x.C, (cuuint64_t)stride, (cuuint64_t)Rs};
-  cuuint64_t astr[2] = {(cuuint64_t)x.C * 4, (cuuint64_t)x.C * 4 * stride};
+  cuuint64_t astr[2] = {(cuuint64_t)x.C * esz, (cuuint64_t)x.C * esz * stride};
   // cluster shape: up to 4 N-tiles x 2 M-tiles share their operand boxes by TMA multicast
   const int tiles_n = (L.N + TC_BN - 1) / TC_BN, tiles_m = (int)((Rs + TC_BM - 1) / TC_BM);
   int cn = 1, cm = 1;
@@ -647,14 +720,20 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   }
   const bool pair = e->tc_pair;   // CTA-pair kernel: (1,2) cluster, each CTA loads half of the B tile
   if (pair) { cn = 1; cm = 2; }
-  cuuint32_t abox[3] = {TC_BK, 1, (cuuint32_t)(pair ? TC_BM : TC_BM / cn)};
-  CUtensorMap mAh = make_map(base_hi, 3, adims, astr, abox), mAl = make_map(base_lo, 3, adims, astr, abox);
+  cuuint32_t abox[3] = {(cuuint32_t)bk, 1, (cuuint32_t)(pair ? TC_BM : TC_BM / cn)};
+  CUtensorMap mAh = make_map(base_hi, 3, adims, astr, abox, f16), mAl = make_map(base_lo, 3, adims, astr, abox, f16);
   cuuint64_t bdims[2] = {(cuuint64_t)L.K, (cuuint64_t)L.N};
-  cuuint64_t bstr[1] = {(cuuint64_t)L.K * 4};
-  cuuint32_t bbox[2] = {TC_BK, (cuuint32_t)(TC_BN / cm)};   // pair: cm == 2 -> 128-row halves
-  CUtensorMap mBh = make_map(onchip ? L.W : L.W_hi, 2, bdims, bstr, bbox), mBl = make_map(onchip ? L.W : L.W_lo, 2, bdims, bstr, bbox);
+  cuuint64_t bstr[1] = {(cuuint64_t)L.K * esz};
+  cuuint32_t bbox[2] = {(cuuint32_t)bk, (cuuint32_t)(TC_BN / cm)};   // pair: cm == 2 -> 128-row halves
+  const void* wh = f16 ? (const void*)L.W_h16 : onchip ? (const void*)L.W : (const void*)L.W_hi;
+  const void* wl = f16 ? (const void*)L.W_l16 : onchip ? (const void*)L.W : (const void*)L.W_lo;
+  CUtensorMap mBh = make_map(wh, 2, bdims, bstr, bbox, f16), mBl = make_map(wl, 2, bdims, bstr, bbox, f16);
   TcArgs P;
-  P.taps = k; P.cblocks = x.C / TC_BK; P.stride = stride; P.C = x.C;
+  P.chunk = 256 / bk;                  // K = 256 per TMEM accumulation chunk
+  P.oscale = f16 ? L.w_unscale : 1.f;
+  P.c_h16 = y.h16 ? y.row_h16(0, y_toff) + coff : nullptr;
+  P.c_l16 = y.h16 ? y.row_l16(0, y_toff) + coff : nullptr;
+  P.taps = k; P.cblocks = x.C / bk; P.stride = stride; P.C = x.C;
   P.rows_in = rows_in; P.off = x.pad - pd; P.T_out = T_out; P.nbatch = x.B; P.Rs = (int)Rs; P.N = L.N;
   P.c_hi = y.row(0, y_toff) + coff; P.c_lo = y.lo ? y.row_lo(0, y_toff) + coff : nullptr;
   P.c_bs = y.bstride(); P.c_rs = (long)y_tmul * y.C;
@@ -665,13 +744,14 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.act = act;
   P.cn = pair ? tiles_n : cn; P.cm = cm;
   { const char* np = getenv("TS_TC_NPROD"); P.nprod = (np && np[0] == '1') ? 1 : (np && np[0] == '4') ? 4 : 3; }
-  P.a_hi = base_hi; P.a_lo = base_lo; P.a_rows = R;
+  P.a_hi = (const float*)base_hi; P.a_lo = (const float*)base_lo; P.a_rows = R;
   // whole-row L2 prefetch measured slower (96 vs 89 ms per face pass): off unless TS_TC_ROWPF=1
-  { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1') ? 1 : 0; }
+  { const char* pf = getenv("TS_TC_ROWPF"); P.prefetch_rows = (pf && pf[0] == '1' && !f16) ? 1 : 0; }
   if (!e->tc_attr_set) {   // the max-dynamic-smem attribute is per device: cached per engine, not per process
     TS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
-    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     e->tc_attr_set = true;
   }
   // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
@@ -687,8 +767,9 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   at[0].val.clusterDim.x = pair ? 2 : cn; at[0].val.clusterDim.y = pair ? 1 : cm; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (pair && onchip) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<true>, mAh, mAl, mBh, mBl, P));
-  else if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false>, mAh, mAl, mBh, mBl, P));
+  if (f16) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false, true>, mAh, mAl, mBh, mBl, P));
+  else if (pair && onchip) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<true, false>, mAh, mAl, mBh, mBl, P));
+  else if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false, false>, mAh, mAl, mBh, mBl, P));
   else TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));
   e->launches++;
   TS_CUDA(cudaGetLastError());
@@ -700,6 +781,10 @@ void upload_weights(ts_engine* e, const std::vector<float>& W, Layer* L) {
   split_host(W, &hi, &lo);
   L->W_hi = e->upload(hi);
   L->W_lo = e->upload(lo);
+  std::vector<unsigned short> h16, l16;
+  L->w_unscale = split16_host(W, &h16, &l16);
+  L->W_h16 = e->upload(h16);
+  L->W_l16 = e->upload(l16);
 }
 
 void conv_auto(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act, const Act3* res,
@@ -715,7 +800,8 @@ using namespace ts;
 extern "C" int ts_set_tensor_cores(ts_engine* e, int enable) {
   if (!e) return TS_ERR_INVALID;
   e->use_tc = enable != 0;
-  e->tc_pair = enable == 1 || enable == 3 || enable == 5;   // 1 (default) / 3 = CTA-pair (cta_group::2) 256x256 kernel
+  e->tc_pair = enable == 1 || enable == 3 || enable == 5 || enable == 6;   // 1 / 3 = CTA-pair (cta_group::2) 256x256 kernel, 3xTF32
+  e->tc_f16 = enable == 6;                   // 6 (default) = the CTA-pair kernel on fp16-split operands (kind::f16, see the file header)
   e->tc_multicast = enable == 2;             // 2 = single-CTA 128x256 kernel in (n x 2) clusters with TMA multicast
                                              // 4 = single-CTA 128x256 kernel, no cluster
   e->tc_onchip = enable == 5;                // 5 = CTA-pair kernel on PLAIN operands, hi / lo split in shared memory (experiment)
@@ -741,9 +827,30 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     Act3 x; x.p = const_cast<float*>(A); x.split = false; x.B = 1; x.T = M; x.C = K; x.pad = 0;
     Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
     tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
+  } else if (mode == 3) {
+    if (K % (2 * TC_BK)) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 64 for the fp16-split path");
+    const bool f0 = e->tc_f16, p0 = e->tc_pair, oc = e->tc_onchip;
+    e->tc_f16 = true; e->tc_pair = true; e->tc_onchip = false;
+    e->ws.sizing = false;
+    unsigned short *ah, *al, *wh, *wl;
+    float* full;
+    TS_CUDA(cudaMalloc(&ah, (size_t)M * K * 2)); TS_CUDA(cudaMalloc(&al, (size_t)M * K * 2));
+    TS_CUDA(cudaMalloc(&wh, (size_t)N * K * 2)); TS_CUDA(cudaMalloc(&wl, (size_t)N * K * 2));
+    TS_CUDA(cudaMalloc(&full, 16));
+    split16_kernel<<<148 * 8, 256, 0, s>>>(A, ah, al, (long)M * K, 1.f);
+    split16_kernel<<<148 * 8, 256, 0, s>>>(W, wh, wl, (long)N * K, 256.f);
+    Layer L;
+    L.N = N; L.K = K; L.taps = 1; L.cin = K; L.W_h16 = wh; L.W_l16 = wl; L.w_unscale = 1.f / 256.f; L.bias = const_cast<float*>(bias);
+    Act3 x; x.p = const_cast<float*>(A); x.h16 = ah; x.l16 = al; x.split = true; x.B = 1; x.T = M; x.C = K; x.pad = 0;
+    Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
+    tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
+    e->tc_f16 = f0; e->tc_pair = p0; e->tc_onchip = oc;
+    TS_CUDA(cudaStreamSynchronize(s));
+    cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl); cudaFree(full);
   } else {
     if (K % TC_BK) fail(TS_ERR_INVALID, "ts_debug_gemm: K must be a multiple of 32 for the tensor-core path");
-    const bool oc = e->tc_onchip;
+    const bool oc = e->tc_onchip, f0 = e->tc_f16;
+    e->tc_f16 = false;
     e->tc_onchip = false;
     e->ws.sizing = false;
     float *ah, *al, *wh, *wl;
@@ -756,7 +863,7 @@ extern "C" int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float
     Act3 x; x.p = ah; x.lo = al; x.split = true; x.B = 1; x.T = M; x.C = K; x.pad = 0;
     Act3 y; y.p = C; y.B = 1; y.T = M; y.C = N; y.pad = 0;
     tc_conv1d(e, L, x, 1, 1, 0, y, M, act, nullptr, s, 1, 0, 0);
-    e->tc_onchip = oc;
+    e->tc_onchip = oc; e->tc_f16 = f0;
     TS_CUDA(cudaStreamSynchronize(s));
     cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
   }

@@ -1,6 +1,9 @@
 // talkshow_b200 — device kernels shared by the conv stacks and the face network (host launchers).
 #pragma once
 #include "common.h"
+#ifdef __CUDACC__
+#include <cuda_fp16.h>
+#endif
 
 namespace ts {
 
@@ -15,9 +18,15 @@ struct Act3 {
   bool split = false;    // stored as (hi, lo) pair, see lo
   float* lo = nullptr;   // when set the activation is stored split for the 3xTF32 tensor-core GEMM:
                          // p = hi part (low 13 mantissa bits clear), lo = x - hi, x == p + lo exactly
+  // fp16-split storage (ts_set_tensor_cores(e, 6), the default): p holds the FULL fp32 value (what every non-tensor-core
+  // reader uses; lo stays null) and the tensor-core GEMM reads the two half planes h16 = fp16(x), l16 = fp16(x - h16)
+  unsigned short* h16 = nullptr;
+  unsigned short* l16 = nullptr;
   __host__ __device__ long bstride() const { return (long)(T + 2 * pad + tail) * C; }
   __host__ __device__ float* row(int b, int t) const { return p + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
   __host__ __device__ float* row_lo(int b, int t) const { return lo + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
+  __host__ __device__ unsigned short* row_h16(int b, int t) const { return h16 + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
+  __host__ __device__ unsigned short* row_l16(int b, int t) const { return l16 + ((long)b * (T + 2 * pad + tail) + pad + t) * C; }
   __host__ __device__ size_t numel() const { return (size_t)B * (T + 2 * pad + tail) * C; }
 };
 
@@ -34,6 +43,8 @@ struct GemmP {
   const float* A_lo = nullptr;  // optional split operands / outputs (x = hi + lo), same indexing as A / R / C
   const float* R_lo = nullptr;
   float* C_lo = nullptr;
+  unsigned short* C_h16 = nullptr;   // fp16-split copy of the output (C itself then holds the full value)
+  unsigned short* C_l16 = nullptr;
   int M = 0, N = 0, K = 0, mper = 1;
   long a_bs = 0, a_rs = 0;
   int kc = 0, a_ts = 0;
@@ -79,6 +90,15 @@ void upload_weights(ts_engine* e, const std::vector<float>& W, Layer* L);
 // conv through the tensor-core kernel when the geometry allows (and e->use_tc), else the FFMA kernel
 void conv_auto(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int pd, const Act3& y, int T_out, int act,
                const Act3* res, cudaStream_t s, int y_tmul = 1, int y_toff = 0, int coff = 0);
+
+#ifdef __CUDACC__
+// two-term fp16 split of an fp32 value: h = fp16(x), l = fp16(x - h) (22 significant bits while l stays normal)
+__device__ __forceinline__ void split16(float x, unsigned short& h, unsigned short& l) {
+  const __half hh = __float2half_rn(x);
+  h = __half_as_ushort(hh);
+  l = __half_as_ushort(__float2half_rn(x - __half2float(hh)));
+}
+#endif
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int pad4(int c) { return (c + 3) & ~3; }

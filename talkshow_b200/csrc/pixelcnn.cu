@@ -27,13 +27,14 @@ namespace ts {
 struct Job {
   int epi, layer, col, nrows, K, ncol;
   bool pairs;
+  int rofs = 0;   // first output row of this job inside the layer's row space (output_conv.2 split over two stages)
 };
 
 // Fused plan: every linear stage of the horizontal stack is folded into the gate matmul that consumes it
 // (W_next (W_res g + b + x) = (W_next W_res) g + W_next b + W_next x), the layer-0 gate of column 0 (no
 // matmul) rides in the last vertical stage, and the layer-0 gate of column 1 is a table lookup done by the
 // sampler itself: 16 + 2 x 18 = 52 dependent stages per row instead of 84.
-static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D) {
+static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D, int out2_split = 1) {
   std::vector<std::vector<Job>> st;
   st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
   st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});
@@ -51,7 +52,8 @@ static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D) {
     for (int l = 2; l < L; ++l)
       st.push_back({{EPI_HGATE2, l, c, 2 * D, c ? 3 * D : 2 * D, 1, true}, {EPI_HRES, l - 1, c, D, D, 1, false}});
     st.push_back({{EPI_OUT1F, 0, c, 512, 2 * D, 1, false}});
-    st.push_back({{EPI_OUT2, 0, c, PIX_NCODE, 512, 1, false}});
+    // output_conv.2 (2048 rows): one stage, or `out2_split` stages when the plan has fewer than 128 CTAs (16 rows per CTA)
+    for (int q = 0; q < out2_split; ++q) st.push_back({{EPI_OUT2, 0, c, PIX_NCODE / out2_split, 512, 1, false, q * (PIX_NCODE / out2_split)}});
     st.push_back({{EPI_SAMPLE, 0, c, 0, c == 0 ? 1 : 0, 1, false}});     // K = 1: also emit G_0 of column 1
   }
   return st;
@@ -219,7 +221,7 @@ struct WeightSrc {
         return hs[l][((size_t)ch * D + ci) * 2 + (sidx == 1 ? 1 : 0)];
       case EPI_OUT1F: return sidx == 0 ? Mo[(size_t)ch * D + ci] : o1[(size_t)ch * D + ci];
       case EPI_OUT1: return o1[(size_t)ch * D + k];
-      case EPI_OUT2: return o2[(size_t)ch * 512 + k];
+      case EPI_OUT2: return o2[(size_t)(ch + j.rofs) * 512 + k];
     }
     return 0.f;
   }
@@ -234,7 +236,7 @@ struct WeightSrc {
       case EPI_HGATE2: return hsb[l][ch] + bh[l][ch];
       case EPI_OUT1F: return o1b[ch] + bo[ch];
       case EPI_OUT1: return o1b[ch];
-      case EPI_OUT2: return o2b[ch];
+      case EPI_OUT2: return o2b[ch + j.rofs];
     }
     return 0.f;  // FUSEV / FUSEH: bias lives in the precomputed audio term
   }
@@ -289,6 +291,9 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
   PixelPlan* P = new PixelPlan();
   P->L = L;
   P->ncta = e->sm_count;
+  // ts_set_pixelcnn_ctas: a plan for FEWER persistent CTAs than SMs leaves whole TPCs free for kernels of another
+  // stream (the face regressor runs beside the latency-bound sampler when the per-GPU batch is small)
+  if (e->pixel_ctas >= PIX_MB && e->pixel_ctas <= e->sm_count) P->ncta = e->pixel_ctas & ~1;
   if (const char* v = getenv("TS_PIX_CTAS")) {   // experiment switch: persistent CTAs (every CTA re-reads the stage's activations from L2)
     const int n = atoi(v);
     if (n >= PIX_MB && n <= e->sm_count) P->ncta = n;
@@ -300,7 +305,9 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
   P->lay = make_layout(L, P->sched == 2 ? L : 2);
   if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);
   P->fused = fused;
-  auto stages = P->sched == 2 ? build_stages_fused2(L) : fused ? build_stages_fused(L) : build_stages(L);
+  const int out2_split = (PIX_NCODE + PIX_MAXROWS * P->ncta - 1) / (PIX_MAXROWS * P->ncta);   // 1 for >= 128 CTAs
+  if (out2_split > 1 && P->sched != 1) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d CTAs need the fused plan", P->ncta);
+  auto stages = P->sched == 2 ? build_stages_fused2(L) : fused ? build_stages_fused(L, PIX_D, out2_split) : build_stages(L);
   P->nstages = (int)stages.size();
   if (P->nstages > 160) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d stages per row (> 160)", P->nstages);
   P->table.assign((size_t)P->nstages * P->ncta, PixTask{0, 0, 0, 0, 0, 0, 0, 0});
@@ -371,7 +378,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
           PixTask t{0, 0, 0, 0, 0, 0, 0, 0};
           if (nu > 0) {
             t.epi = j.epi; t.layer = j.layer; t.col = j.col;
-            t.row0 = u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
+            t.row0 = j.rofs + u0 * unit; t.nrows = nu * unit; t.K = j.K; t.rpad = (t.nrows + 3) & ~3;
             if (t.K > 0 && t.nrows > rowcap) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d rows per unit (> %d) with %d SMs", t.nrows, rowcap, P->ncta);
             const int Ks = t.K / cl, k0 = rank * Ks;       // K is a multiple of 256
             size_t sz = (size_t)(Ks + 1) * t.rpad;
@@ -380,8 +387,8 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
             P->blob.resize(P->blob.size() + sz, 0.f);
             float* dst = P->blob.data() + t.wofs;
             for (int r = 0; r < t.nrows; ++r) {
-              for (int k = 0; k < Ks; ++k) dst[(size_t)k * t.rpad + r] = ws.w(j, t.row0 + r, k0 + k);
-              dst[(size_t)Ks * t.rpad + r] = ws.bias(j, t.row0 + r);
+              for (int k = 0; k < Ks; ++k) dst[(size_t)k * t.rpad + r] = ws.w(j, t.row0 - j.rofs + r, k0 + k);
+              dst[(size_t)Ks * t.rpad + r] = ws.bias(j, t.row0 - j.rofs + r);
             }
             dense += (int64_t)t.nrows * Ks;
           }
@@ -1173,7 +1180,7 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
   PixelPlan* P = e->pix;
   Plan3* Q = (Plan3*)P->p3;
   const int Ttot = T0 + T, D = P->D;
-  const bool v3 = e->pixel_mode == 2 || !P->has_v1;
+  const bool v3 = (e->pixel_mode == 2 && Q) || !P->has_v1;
   // audio terms for all rows of this chunk: three GEMMs over B*Ttot rows
   float* a_emb = e->ws.alloc<float>((size_t)B * Ttot * D);
   float* audv = e->ws.alloc<float>((size_t)B * Ttot * D);
@@ -1237,7 +1244,25 @@ static void generate_chunk(ts_engine* e, const Act3& aud, int b0, const int64_t*
     int rs = 0, ss = 0;
     void* args[] = {&A, &rs, &ss};
     if (P->timing) TS_CUDA(cudaEventRecord(P->ev0, s));
-    TS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
+    if (P->ncta < e->sm_count && (P->ncta & 1) == 0) {
+      // partial-GPU plan: launched as CTA pairs (cluster 2x1x1) so that the kernel fills whole TPCs and the remaining TPCs
+      // stay entirely free — the tcgen05 CTA-pair GEMMs of the face path need both SMs of a TPC
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(P->ncta);
+      cfg.blockDim = dim3(PIX_THREADS);
+      cfg.dynamicSmemBytes = PIX_SMEM;
+      cfg.stream = s;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative;
+      at[1].val.cooperative = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 2;
+      TS_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    } else {
+      TS_CUDA(cudaLaunchCooperativeKernel(fn, dim3(P->ncta), dim3(PIX_THREADS), args, PIX_SMEM, s));
+    }
     if (P->timing) { TS_CUDA(cudaEventRecord(P->ev1, s)); P->timed_rows += Ttot; P->timed_launches++; P->pending = true; }
     e->launches++;
   } else {
@@ -1289,7 +1314,8 @@ extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
   std::unique_ptr<PixelPlan> P(D == PIX_D ? build_plan(e, ck, e->pixel_fusion) : new PixelPlan());
   P->L = L; P->D = D; P->nclasses = ncls;
   plan_common(e, ck, P.get(), L, D);
-  Plan3* Q = build_plan3(e, ck, L, D, ncls);
+  // an engine set up for a partial-GPU grid-wide plan (ts_set_pixelcnn_ctas) does not need the cluster-resident plan as well
+  Plan3* Q = (P->has_v1 && e->pixel_ctas > 0) ? nullptr : build_plan3(e, ck, L, D, ncls);
   P->p3 = Q;
   if (!P->has_v1) { P->nstages = Q->nstages; P->ncta = C3_CL; }
   pixel_destroy(e);
@@ -1301,7 +1327,7 @@ extern "C" int ts_load_pixelcnn(ts_engine* e, const ts_tensor* tensors, int n) {
 extern "C" int64_t ts_pixelcnn_row_bytes(ts_engine* e) { return (e && e->pix) ? e->pix->row_bytes : 0; }
 extern "C" int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e) {
   if (!e || !e->pix) return 0;
-  if (e->pixel_mode == 2 || !e->pix->has_v1) return (int64_t)((Plan3*)e->pix->p3)->rank_stride * C3_CL * 4;
+  if ((e->pixel_mode == 2 && e->pix->p3) || !e->pix->has_v1) return (int64_t)((Plan3*)e->pix->p3)->rank_stride * C3_CL * 4;
   return e->pix->staged_row_bytes;
 }
 

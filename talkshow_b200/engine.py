@@ -95,6 +95,10 @@ class Engine:
         2 fused with vert_to_horiz scheduled in the horizontal pass (experimental)."""
         self._check(self.L.ts_set_pixelcnn_fusion(self.h, int(on)), "ts_set_pixelcnn_fusion")
 
+    def set_pixelcnn_ctas(self, n):
+        """Persistent CTAs of the grid-wide sampler plan built by the next load_pixelcnn (0 = one per SM)."""
+        self._check(self.L.ts_set_pixelcnn_ctas(self.h, int(n)), "ts_set_pixelcnn_ctas")
+
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
 

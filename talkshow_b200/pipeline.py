@@ -22,11 +22,21 @@ def shard_range(B, rank, world):
 
 
 class WholeBody:
-    """face (jaw+expression) + body/hands + part2full assembly -> SMPL-X parameters [B,F,265]."""
+    """face (jaw+expression) + body/hands + part2full assembly -> SMPL-X parameters [B,F,265].
 
-    def __init__(self, engine: Engine):
+    ``overlap_batch`` > 0: batches up to that size run the body path and the face path SIDE BY SIDE on two streams.  With
+    few clips per GPU both halves are latency-bound and leave most of the machine idle (the sampler is a serial chain of
+    3 900 stages, the face GEMMs have fewer tiles than SMs), so a second engine holds a sampler plan for ``overlap_ctas``
+    persistent CTAs launched as CTA pairs (whole TPCs), and the face kernels fill the remaining TPCs.  Results are
+    bit-identical to the sequential order (same kernels, same arithmetic)."""
+
+    def __init__(self, engine: Engine, overlap_batch=8, overlap_ctas=100):
         self.e = engine
         self.device = engine.device
+        self.overlap_batch = overlap_batch if not getattr(engine, "host_only", True) else 0
+        self.overlap_ctas = overlap_ctas
+        self.e2 = None            # body path engine with the partial-GPU sampler plan (same device)
+        self._side = None
 
     def load(self, pixel_ckpt, vq_ckpt, face_ckpt):
         """Checkpoint dicts in the reference's formats (talkshow_b200/synth.py docstring)."""
@@ -35,6 +45,22 @@ class WholeBody:
         self.e.load_vq(0, vq_ckpt["g_body"])
         self.e.load_vq(1, vq_ckpt["g_hand"])
         self.e.load_face(face_ckpt["generator"])
+        dim = pixel_ckpt["generator"]["embedding.weight"].shape[1]
+        if self.overlap_batch > 0 and dim == 256 and self.overlap_ctas < self.e.sm_count:
+            idx = self.device.index or 0
+            self.e2 = Engine(idx)
+            self.e2.set_pixelcnn_ctas(self.overlap_ctas)
+            self.e2.load_pixelcnn(pixel_ckpt["generator"])
+            self.e2.load_audioenc(pixel_ckpt["audioencoder"])
+            self.e2.load_vq(0, vq_ckpt["g_body"])
+            self.e2.load_vq(1, vq_ckpt["g_hand"])
+            self._side = torch.cuda.Stream(device=self.device)
+
+    def close(self):
+        if self.e2 is not None:
+            torch.cuda.synchronize(self.device)
+            self.e2.close()
+            self.e2 = None
 
     def generate(self, mfcc, wave, label, noise=None, stand=False, per_step_noise=True):
         """mfcc [B,64,M], wave [B,N] (16 kHz), label [B] on the device -> poses [B,F,265] (device).
@@ -44,7 +70,21 @@ class WholeBody:
         T = self.e.latent_rows(M)
         if noise is None:
             noise = draw_sampler_noise(T, B, self.device, per_step=per_step_noise)
-        face = self.e.face_forward(wave, torch.zeros(B, 4, device=self.device), frame)   # demo.py:173-181: id not passed
+        idz = torch.zeros(B, 4, device=self.device)                    # demo.py:173-181: id not passed
+        if self.e2 is not None and B <= self.overlap_batch:
+            # small batch: sampler (on overlap_ctas SMs, launched first) and face regressor (on the free TPCs) side by side
+            cur = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                _, body = self.e2.body_generate(mfcc, label, noise, want_codes=False)
+            face = self.e.face_forward(wave, idz, frame)
+            cur.wait_stream(self._side)
+            body.record_stream(cur)                                      # allocated on the side stream, consumed here
+            for t in (mfcc, label, noise):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(self._side)                          # allocated here, consumed on the side stream
+            return self.e.assemble_pose(face, body, stand)
+        face = self.e.face_forward(wave, idz, frame)
         _, body = self.e.body_generate(mfcc, label, noise, want_codes=False)
         return self.e.assemble_pose(face, body, stand)
 

@@ -139,3 +139,35 @@ def test_sharded_equals_unsharded(wb, B, world):
     body_cols = list(range(3, 165))
     assert torch.equal(got[:, :, body_cols], full[:, :, body_cols])          # sampler + VQ decoders: bit-identical
     assert (got - full).abs().max().item() <= 1e-5                           # face GEMM tiles depend on the batch size
+
+
+def test_overlapped_small_batch_equals_sequential(ckpts):
+    """8 clips per GPU (config 5 on 8 GPUs): the body path on a 100-CTA sampler plan and the face path run side by side on
+    two streams; the result is bit-identical to the sequential order."""
+    from talkshow_b200.engine import Engine
+    from talkshow_b200.pipeline import WholeBody
+
+    B, M = 8, 300
+    mfcc = synth.synth_mfcc(B, M, seed=901).cuda()
+    wave = synth.synth_wave(B, 160000, seed=902).cuda()
+    label = (torch.arange(B) % 4).cuda()
+    noise = draw_noise(2 * O.latent_rows(M), B, 903).cuda()
+    outs = []
+    for ob in (0, 8):
+        e = Engine(0)
+        w = WholeBody(e, overlap_batch=ob)
+        w.load(ckpts["pixel"], ckpts["vq"], ckpts["face"])
+        assert (w.e2 is not None) == (ob > 0)
+        for _ in range(2):
+            out = w.generate(mfcc, wave, label, noise=noise)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); out = w.generate(mfcc, wave, label, noise=noise); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print("whole body, 8 clips x 10 s, overlap_batch=%d: %.2f ms per step" % (ob, min(ts)))
+        outs.append(out.clone())
+        w.close()
+        e.close()
+    assert torch.equal(outs[0], outs[1])
