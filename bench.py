@@ -369,13 +369,14 @@ def run_ours(args, rank, world, local_rank):
                 "algorithmic_bytes": alg_bytes, "share_of_step": pix_avg / (dev_ms / args.steps)}
     # 106 GFLOP per 10 s clip (53 GMAC), scaled with the clip length
     face_flop = 106.0e9 * main.b * args.seconds / 10.0
-    tf32x3_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0 / 3.0     # tf32 rate = bf16/2, three products per MAC
+    # fp32-grade MACs as three kind::f16 products on fp16-split operands (the default since r02; 3xTF32 would be bf16/2/3)
+    tf32x3_peak = float(peaks.get("bf16_tflops", 1590.0)) / 3.0
     roofline_dense = None
     if face_avg > 0:
-        roofline_dense = {"kernel": "face path (tc2_gemm_kernel tcgen05 3xTF32 + HMMA attention + FFMA2 layers per forward)",
+        roofline_dense = {"kernel": "face path (tc2_gemm_kernel<fp16-split> tcgen05 kind::f16 x3 + HMMA attention + FFMA2 layers per forward)",
                           "bound": "tensor", "achieved": face_flop / (face_avg * 1e-3) / 1e12, "peak": tf32x3_peak, "unit": "TFLOP/s",
                           "frac": face_flop / (face_avg * 1e-3) / 1e12 / tf32x3_peak,
-                          "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32) / 3 (3xTF32 split)" if peaks else "fallback 1590/6",
+                          "peak_source": "MEASURED_PEAKS.json bf16_tflops / 3 (three f16 products per fp32-grade MAC)" if peaks else "fallback 1590/3",
                           "traffic": None, "launch_ms": face_avg, "share_of_step": face_avg / (dev_ms / args.steps)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

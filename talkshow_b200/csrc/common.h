@@ -135,7 +135,7 @@ struct ts_engine {
   int pixel_fusion = 1;      // plan built at ts_load_pixelcnn: 0 plain 84-stage, 1 fused 52-stage, 2 fused + vert_to_horiz in the horizontal pass
   bool tc_pair = true;       // CTA-pair (cta_group::2) 256x256 tensor-core kernel (default)
   bool tc_onchip = false;    // experiment (mode 5): CTA-pair kernel takes plain fp32 operands and splits them hi / lo in shared memory
-  bool tc_f16 = false;       // CTA-pair kernel on fp16-split operands (kind::f16, 3 products at twice the tf32 rate)
+  bool tc_f16 = true;        // default: CTA-pair kernel on fp16-split operands (kind::f16, 3 products at twice the tf32 rate)
   bool tc_multicast = false;  // share operand boxes inside a thread-block cluster by TMA multicast
   bool tc_attr_set = false;  // cudaFuncSetAttribute(max dynamic smem) of the tcgen05 kernels done on this engine's device
   bool use_tc = true;  // dense contractions on the tcgen05 3xTF32 kernel when the geometry allows
