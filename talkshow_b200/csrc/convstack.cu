@@ -165,7 +165,7 @@ void pack_vq(ts_engine* e, const Ckpt& ck, VQNet* v) {
 }
 
 // ---- execution -------------------------------------------------------------------------------
-Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool split, int tail) {
+Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool split, int tail, bool planes_only) {
   Act3 a;
   a.B = B;
   a.T = T;
@@ -173,7 +173,8 @@ Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool sp
   a.pad = pad;
   a.tail = tail;
   a.split = split;
-  a.p = e->ws.alloc<float>(a.numel());
+  // planes_only: the activation feeds tensor-core convs only -- no fp32 copy (half the bytes written and kept)
+  if (!(planes_only && split && e->tc_f16 && e->use_tc && e->tc_pair)) a.p = e->ws.alloc<float>(a.numel());
   if (split && e->tc_f16) {
     a.h16 = e->ws.alloc<unsigned short>(a.numel());
     a.l16 = e->ws.alloc<unsigned short>(a.numel());

@@ -33,7 +33,7 @@ struct ConvStacks {
 
 void pack_trunk(ts_engine* e, const Ckpt& ck, const std::string& p, int in_dim, int hid, Trunk* t);
 void pack_vq(ts_engine* e, const Ckpt& ck, VQNet* v);
-Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool split = false, int tail = 0);
+Act3 new_act(ts_engine* e, int B, int T, int C, int pad, cudaStream_t s, bool split = false, int tail = 0, bool planes_only = false);
 Act3 run_trunk(ts_engine* e, const Trunk& t, const Act3& x, cudaStream_t s);
 Act3 run_decoder(ts_engine* e, const VQNet& v, const Act3& q, cudaStream_t s);
 Act3 run_vq_decode(ts_engine* e, const VQNet& v, const int64_t* idx, int B, int T, cudaStream_t s);

@@ -26,6 +26,8 @@ struct FaceNet {
   Layer conv[7];  // 1..6 used
   float *fp_ln_g = nullptr, *fp_ln_b = nullptr;
   Layer fproj, posconv;
+  unsigned short* pos_w16 = nullptr;   // posconv_mma_kernel's pre-split weights
+  float pos_unscale = 1.f;
   float *enc_ln_g = nullptr, *enc_ln_b = nullptr;
   std::vector<EncLayer> layers;
   Layer feat_map;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
       float v = (y - mu) * rstd * gg + bb;
       v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
       if (out.h16) {
-        out.row(b, t0 + t)[c] = v;
+        if (out.p) out.row(b, t0 + t)[c] = v;
         split16(v, out.row_h16(b, t0 + t)[c], out.row_l16(b, t0 + t)[c]);
       } else if (out.lo) {
         float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
@@ -1009,6 +1011,159 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 1) attention_mma16t_kernel(con
 }
 
 
+// ---- positional conv embedding (Conv1d 768 -> 768, k = 128, groups = 16, pad 64) on HMMA ---------------------------
+// Per (clip, group) the conv is a [T x 6144] Toeplitz matrix times a [6144 x 48] weight block: N = 48 is too narrow for a
+// tcgen05 tile, and as an fp32 FFMA GEMM it cost 6.3 ms of the 45 ms face forward.  Here one CTA owns 320 output rows of
+// one (clip, group): the group's 48 input channels of the 447-row window are split ONCE into two fp16 planes in shared
+// memory (x = h + l, as everywhere else), a tap is a row shift of the window (A fragments are plain 32-bit shared loads at
+// row m + tap), the weights arrive pre-split and pre-scaled in 4-tap chunks through a cp.async double buffer, and every
+// (tap, 16-channel) step is 3 HMMA m16n8k16 per 16 x 8 output block (l*h + h*l + h*h).  Each chunk accumulates into fresh
+// fp32 accumulators that are then added (round-to-nearest) to the running sum: the tensor core's accumulator truncates.
+constexpr int PC_WARPS = 10, PC_MT = 2;
+constexpr int PC_ROWS = PC_WARPS * PC_MT * 16;      // 320 output rows per CTA
+constexpr int PC_XR = PC_ROWS + 128;                // window rows (127-row halo)
+constexpr int PC_LD = 56;                           // row stride in halves (48 + 8 pad = 28 words: fragment loads conflict-free)
+constexpr int PC_TAPS = 4;                          // taps per weight chunk
+constexpr int PC_WCH = PC_TAPS * 2 * 48 * PC_LD;    // halves per chunk: [tap][plane][n][PC_LD]
+constexpr size_t PC_SMEM = ((size_t)2 * PC_XR * PC_LD + (size_t)2 * PC_WCH) * sizeof(unsigned short);
+
+__global__ void __launch_bounds__(PC_WARPS * 32, 1) posconv_mma_kernel(Act3 x, const unsigned short* __restrict__ W16,
+                                                                       const float* __restrict__ bias, float unscale, Act3 out) {
+  extern __shared__ __align__(16) unsigned short pcs[];
+  unsigned short* Xh = pcs;
+  unsigned short* Xl = Xh + PC_XR * PC_LD;
+  unsigned short* Wb = Xl + PC_XR * PC_LD;          // two chunk buffers
+  const int b = blockIdx.x / 16, grp = blockIdx.x % 16, t0 = blockIdx.y * PC_ROWS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int T = out.T;
+  const unsigned short* wsrc = W16 + (size_t)grp * 128 * 2 * 48 * PC_LD;
+  auto fetch = [&](int ch) {
+    const unsigned short* src = wsrc + (size_t)ch * PC_WCH;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Wb + (ch & 1) * PC_WCH);
+    for (int i = tid; i < PC_WCH / 8; i += PC_WARPS * 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i * 8) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(0);
+  // window row r holds time t0 + r - 64 (the conv's left padding of 64 lives in the activation's pad rows)
+  for (int i = tid; i < PC_XR * 12; i += PC_WARPS * 32) {
+    const int r = i / 12, c4 = (i - r * 12) * 4, tt = t0 + r - 64;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt < T + 64) v = *reinterpret_cast<const float4*>(x.row(b, tt) + grp * 48 + c4);
+    uint32_t h0, l0, h1, l1;
+    split_h2(v.x, v.y, h0, l0);
+    split_h2(v.z, v.w, h1, l1);
+    *reinterpret_cast<uint2*>(Xh + r * PC_LD + c4) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(Xl + r * PC_LD + c4) = make_uint2(l0, l1);
+  }
+  float acc[PC_MT][6][4];
+#pragma unroll
+  for (int mt = 0; mt < PC_MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 6; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  bool live[PC_MT];
+#pragma unroll
+  for (int mt = 0; mt < PC_MT; ++mt) live[mt] = t0 + (warp * PC_MT + mt) * 16 < T;   // warp-uniform
+
+  for (int ch = 0; ch < 128 / PC_TAPS; ++ch) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                 // chunk ch landed; every warp is done with chunk ch - 1 (and, first time, the window is filled)
+    if (ch + 1 < 128 / PC_TAPS) fetch(ch + 1);
+    const unsigned short* Wc = Wb + (ch & 1) * PC_WCH;
+    float fa[PC_MT][6][4];
+#pragma unroll
+    for (int mt = 0; mt < PC_MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) fa[mt][nt][0] = fa[mt][nt][1] = fa[mt][nt][2] = fa[mt][nt][3] = 0.f;
+#pragma unroll 1
+    for (int tp = 0; tp < PC_TAPS; ++tp) {
+      const int k = ch * PC_TAPS + tp;
+      const unsigned short* Wh = Wc + (size_t)tp * 2 * 48 * PC_LD;
+      const unsigned short* Wl = Wh + 48 * PC_LD;
+#pragma unroll
+      for (int cs = 0; cs < 3; ++cs) {
+        const int c0 = cs * 16 + 2 * t;
+        uint32_t bh0[6], bh1[6], bl0[6], bl1[6];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const int w = (nt * 8 + g) * PC_LD + c0;
+          bh0[nt] = *reinterpret_cast<const uint32_t*>(Wh + w); bh1[nt] = *reinterpret_cast<const uint32_t*>(Wh + w + 8);
+          bl0[nt] = *reinterpret_cast<const uint32_t*>(Wl + w); bl1[nt] = *reinterpret_cast<const uint32_t*>(Wl + w + 8);
+        }
+#pragma unroll
+        for (int mt = 0; mt < PC_MT; ++mt) {
+          if (!live[mt]) continue;
+          const int r = (warp * PC_MT + mt) * 16 + g + k;
+          uint32_t ah[4], al[4];
+          ah[0] = *reinterpret_cast<const uint32_t*>(Xh + r * PC_LD + c0);       al[0] = *reinterpret_cast<const uint32_t*>(Xl + r * PC_LD + c0);
+          ah[1] = *reinterpret_cast<const uint32_t*>(Xh + (r + 8) * PC_LD + c0); al[1] = *reinterpret_cast<const uint32_t*>(Xl + (r + 8) * PC_LD + c0);
+          ah[2] = *reinterpret_cast<const uint32_t*>(Xh + r * PC_LD + c0 + 8);   al[2] = *reinterpret_cast<const uint32_t*>(Xl + r * PC_LD + c0 + 8);
+          ah[3] = *reinterpret_cast<const uint32_t*>(Xh + (r + 8) * PC_LD + c0 + 8);
+          al[3] = *reinterpret_cast<const uint32_t*>(Xl + (r + 8) * PC_LD + c0 + 8);
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) mma_f16(fa[mt][nt], al, bh0[nt], bh1[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) mma_f16(fa[mt][nt], ah, bl0[nt], bl1[nt]);
+#pragma unroll
+          for (int nt = 0; nt < 6; ++nt) mma_f16(fa[mt][nt], ah, bh0[nt], bh1[nt]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < PC_MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        acc[mt][nt][0] += fa[mt][nt][0]; acc[mt][nt][1] += fa[mt][nt][1];
+        acc[mt][nt][2] += fa[mt][nt][2]; acc[mt][nt][3] += fa[mt][nt][3];
+      }
+  }
+#pragma unroll
+  for (int mt = 0; mt < PC_MT; ++mt) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int row = t0 + (warp * PC_MT + mt) * 16 + g + half * 8;
+      if (row >= T) continue;
+      float* orow = out.row(b, row) + grp * 48;
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        const int n = nt * 8 + 2 * t;
+        float v0 = acc[mt][nt][half * 2] * unscale + bias[grp * 48 + n];
+        float v1 = acc[mt][nt][half * 2 + 1] * unscale + bias[grp * 48 + n + 1];
+        v0 = 0.5f * v0 * (1.0f + erff(v0 * 0.70710678118654752440f));
+        v1 = 0.5f * v1 * (1.0f + erff(v1 * 0.70710678118654752440f));
+        *reinterpret_cast<float2*>(orow + n) = make_float2(v0, v1);
+      }
+    }
+  }
+}
+
+// host pack of pos_conv_embed.conv.weight [768][48][128] -> fp16 planes [group][tap][plane][n][PC_LD] of W * 2^shift
+static unsigned short* pack_posconv16(ts_engine* e, const float* w, float* unscale) {
+  float mx = 0.f;
+  for (size_t i = 0; i < (size_t)768 * 48 * 128; ++i) mx = std::max(mx, std::fabs(w[i]));
+  int shift = 0;
+  if (mx > 0.f && std::isfinite(mx)) {
+    int ex;
+    std::frexp(mx, &ex);
+    shift = std::min(14, std::max(0, 14 - ex));
+  }
+  const float sc = std::ldexp(1.0f, shift);
+  *unscale = std::ldexp(1.0f, -shift);
+  std::vector<unsigned short> P((size_t)16 * 128 * 2 * 48 * PC_LD, 0);
+  for (int grp = 0; grp < 16; ++grp)
+    for (int k = 0; k < 128; ++k)
+      for (int n = 0; n < 48; ++n)
+        for (int c = 0; c < 48; ++c) {
+          const float v = w[((size_t)(grp * 48 + n) * 48 + c) * 128 + k] * sc;
+          const __half h = __float2half_rn(v);
+          const __half l = __float2half_rn(v - __half2float(h));
+          const size_t at = ((((size_t)grp * 128 + k) * 2) * 48 + n) * PC_LD + c;
+          P[at] = __half_as_ushort(h);
+          P[at + (size_t)48 * PC_LD] = __half_as_ushort(l);
+        }
+  return e->upload(P);
+}
+
 static void attention(ts_engine* e, const float* qkv, const Act3& o, int B, int T, int H, cudaStream_t s) {
   if (e->ws.sizing) return;
   float* out = o.p;
@@ -1090,7 +1245,7 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   int T = (N - 10) / 5 + 1;
   double* stats = e->ws.alloc<double>((size_t)B * 512 * 2);
   const bool tc = e->use_tc && !(e->tc_pair && e->tc_onchip);   // activations stored split (hi, lo) only for the pre-split kernels
-  Act3 h = new_act(e, B, T, 512, 0, s, tc, T & 1);     // rows per batch even for the stride-2 convs
+  Act3 h = new_act(e, B, T, 512, 0, s, tc, T & 1, true);     // rows per batch even for the stride-2 convs; read by tensor-core convs only
   if (!e->ws.sizing) {
     TS_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * 512 * 2 * sizeof(double), s));
     conv0_stats_kernel<<<dim3(cdiv(T, 256), B), 256, 0, s>>>(wave, F.conv0_w, N, T, stats);
@@ -1100,7 +1255,7 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   }
   for (int i = 1; i < 7; ++i) {
     int To = (T - W2V_K[i]) / W2V_S[i] + 1;
-    Act3 y = new_act(e, B, To, 512, 0, s, tc && i < 6, To & 1);   // conv6 output feeds the interpolation: plain
+    Act3 y = new_act(e, B, To, 512, 0, s, tc && i < 6, To & 1, true);   // conv6 output feeds the interpolation: plain
     conv_auto(e, F.conv[i], h, W2V_K[i], W2V_S[i], 0, y, To, ACT_GELU, nullptr, s);
     h = y;
     T = To;
@@ -1119,7 +1274,14 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
   linear(e, F.fproj, hn, x, ACT_NONE, nullptr, s);
   // ---- positional conv embedding (k=128, groups=16, pad 64, last output dropped) + LN -----------
   Act3 pc = new_act(e, B, frame, 768, 0, s);
-  {
+  if (e->use_tc && F.pos_w16) {
+    if (!e->ws.sizing) {
+      TS_CUDA(cudaFuncSetAttribute(posconv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+      posconv_mma_kernel<<<dim3(B * 16, cdiv(frame, PC_ROWS)), PC_WARPS * 32, PC_SMEM, s>>>(x, F.pos_w16, F.posconv.bias, F.pos_unscale, pc);
+      e->launches++;
+      TS_CUDA(cudaGetLastError());
+    }
+  } else {
     GemmP p;
     p.A = x.row(0, -64); p.W = F.posconv.W; p.bias = F.posconv.bias; p.C = pc.row(0, 0);
     p.M = B * frame; p.N = 48; p.K = 128 * 48; p.mper = frame;
@@ -1204,6 +1366,7 @@ extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
   const std::string en = a + "encoder.";
   F->posconv = pack_ckc(e, ck.f32(en + "pos_conv_embed.conv.weight", {768, 48, 128}), ck.f32(en + "pos_conv_embed.conv.bias", {768}),
                         768, 48, 128);
+  F->pos_w16 = pack_posconv16(e, ck.f32(en + "pos_conv_embed.conv.weight", {768, 48, 128}), &F->pos_unscale);
   F->enc_ln_g = up(e, ck.f32(en + "layer_norm.weight", {768}), 768);
   F->enc_ln_b = up(e, ck.f32(en + "layer_norm.bias", {768}), 768);
   for (int l = 0; ck.has(en + "layers." + std::to_string(l) + ".attention.q_proj.weight"); ++l) {

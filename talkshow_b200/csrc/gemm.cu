@@ -222,6 +222,7 @@ void conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, int 
             const Act3* res, cudaStream_t s, int y_tmul, int y_toff, int x_toff, int coff) {
   if (L.taps != k || L.cin != x.C) fail(TS_ERR_INVALID, "conv1d: layer (taps %d, cin %d) vs input (k %d, C %d)", L.taps, L.cin, k, x.C);
   if (x.pad < pd) fail(TS_ERR_INVALID, "conv1d: input pad %d < conv pad %d", x.pad, pd);
+  if (!e->ws.sizing && (!x.p || !y.p)) fail(TS_ERR_INVALID, "conv1d: activation without an fp32 copy (fp16 planes only) on the FFMA path");
   GemmP p;
   p.A = x.row(0, 0) + (long)(x_toff - pd) * x.C;
   if (x.lo) p.A_lo = x.row_lo(0, 0) + (long)(x_toff - pd) * x.C;
@@ -306,7 +307,7 @@ __global__ void zero_pads_kernel(Act3 a) {
     int b = i / per, r = i % per;
     int row = r / a.C, c = r % a.C;
     int t = row < a.pad ? row - a.pad : a.T + (row - a.pad);
-    a.row(b, t)[c] = 0.f;
+    if (a.p) a.row(b, t)[c] = 0.f;
     if (a.lo) a.row_lo(b, t)[c] = 0.f;
     if (a.h16) { a.row_h16(b, t)[c] = 0; a.row_l16(b, t)[c] = 0; }
   }

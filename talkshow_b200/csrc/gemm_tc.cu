@@ -245,7 +245,8 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem
       }
     }
     if (P.c_h16) {
-      for (int q = 0; q < 4 && n + q < P.N; ++q) P.c_hi[coff + q] = o[q];
+      if (P.c_hi)
+        for (int q = 0; q < 4 && n + q < P.N; ++q) P.c_hi[coff + q] = o[q];
       if (n + 3 < P.N) {
         ushort4 h, l;
         split16(o[0], h.x, l.x); split16(o[1], h.y, l.y); split16(o[2], h.z, l.z); split16(o[3], h.w, l.w);
@@ -700,6 +701,7 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
                cudaStream_t s, int y_tmul, int y_toff, int coff) {
   if (e->ws.sizing) return;
   if (!tc_conv_supported(e, L, x, stride, pd)) fail(TS_ERR_INVALID, "tc_conv1d: unsupported geometry");
+  if (!y.p && !y.h16) fail(TS_ERR_INVALID, "tc_conv1d: output without storage");
   const bool onchip = e->tc_pair && e->tc_onchip;
   const bool f16 = e->tc_pair && e->tc_f16;
   const int esz = f16 ? 2 : 4, bk = f16 ? 2 * TC_BK : TC_BK;
@@ -735,7 +737,7 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
   P.c_l16 = y.h16 ? y.row_l16(0, y_toff) + coff : nullptr;
   P.taps = k; P.cblocks = x.C / bk; P.stride = stride; P.C = x.C;
   P.rows_in = rows_in; P.off = x.pad - pd; P.T_out = T_out; P.nbatch = x.B; P.Rs = (int)Rs; P.N = L.N;
-  P.c_hi = y.row(0, y_toff) + coff; P.c_lo = y.lo ? y.row_lo(0, y_toff) + coff : nullptr;
+  P.c_hi = y.p ? y.row(0, y_toff) + coff : nullptr; P.c_lo = y.lo ? y.row_lo(0, y_toff) + coff : nullptr;
   P.c_bs = y.bstride(); P.c_rs = (long)y_tmul * y.C;
   P.bias = L.bias;
   P.r_hi = res ? res->row(0, 0) : nullptr;
