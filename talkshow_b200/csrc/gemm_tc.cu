@@ -176,6 +176,83 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 //     instructions of code instead of a 10k-instruction unrolled epilogue (the first version spent 30 % of
 //     its warp samples in instruction-fetch stalls).
 constexpr int TC_SLD = TC_BN + 4;   // padded row of the parked tile (floats)
+
+// Write-out of the parked tile.  Thread -> 4 fixed columns (bias loaded once), rows strided by 4; the first version did the
+// row / column arithmetic, a runtime activation switch and scalar tails per element: ~420 instructions per float4, 28 us
+// per tile -- more than a K = 768 tile's whole main loop (ncu, profiles/r02_gemm_f16_ncu_summary.md).
+template <int ACT>
+__device__ __forceinline__ void tc_writeout(const TcArgs& P, const float* S, const long* rowc, const long* rowr, int n0) {
+  const int et = threadIdx.x - 128;
+  const int c4 = (et & 63) * 4, n = n0 + c4;
+  if (n >= P.N) return;
+  const int nv = min(4, P.N - n);                   // valid columns of this thread (4 except at a ragged N edge)
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (P.bias)
+    for (int q = 0; q < nv; ++q) bv[q] = P.bias[n + q];
+  const float osc = P.oscale;
+  const bool rvec = nv == 4 && P.r_hi && (((P.r_bs | P.r_rs) & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.r_hi) & 15) == 0) &&
+                    (!P.r_lo || (reinterpret_cast<uintptr_t>(P.r_lo) & 15) == 0);
+#pragma unroll 4
+  for (int r = et >> 6; r < TC_BM; r += 4) {
+    const long co = rowc[r];
+    if (co < 0) continue;
+    const float4 sv = *reinterpret_cast<const float4*>(&S[r * TC_SLD + c4]);
+    float o[4] = {sv.x * osc + bv[0], sv.y * osc + bv[1], sv.z * osc + bv[2], sv.w * osc + bv[3]};
+    if (P.r_hi) {
+      const long roff = rowr[r] + n;
+      if (rvec) {
+        const float4 rh = *reinterpret_cast<const float4*>(P.r_hi + roff);
+        if (P.r_lo) {
+          const float4 rl = *reinterpret_cast<const float4*>(P.r_lo + roff);
+          o[0] += rh.x + rl.x; o[1] += rh.y + rl.y; o[2] += rh.z + rl.z; o[3] += rh.w + rl.w;
+        } else {
+          o[0] += rh.x; o[1] += rh.y; o[2] += rh.z; o[3] += rh.w;
+        }
+      } else {
+        for (int q = 0; q < nv; ++q) o[q] += P.r_lo ? (P.r_hi[roff + q] + P.r_lo[roff + q]) : P.r_hi[roff + q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ACT == ACT_GELU) o[q] = 0.5f * o[q] * (1.0f + erff(o[q] * 0.70710678118654752440f));
+      else if (ACT != ACT_NONE) o[q] = tc_act(o[q], P.act);
+    }
+    const long coff = co + n;
+    if (nv == 4) {
+      if (P.c_h16) {
+        if (P.c_hi) *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
+        ushort4 h, l;
+        split16(o[0], h.x, l.x); split16(o[1], h.y, l.y); split16(o[2], h.z, l.z); split16(o[3], h.w, l.w);
+        *reinterpret_cast<ushort4*>(P.c_h16 + coff) = h;
+        *reinterpret_cast<ushort4*>(P.c_l16 + coff) = l;
+      } else if (P.c_lo) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
+        h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
+        h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
+        h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
+        *reinterpret_cast<float4*>(P.c_hi + coff) = h;
+        *reinterpret_cast<float4*>(P.c_lo + coff) = l;
+      } else {
+        *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      for (int q = 0; q < nv; ++q) {
+        if (P.c_h16) {
+          if (P.c_hi) P.c_hi[coff + q] = o[q];
+          split16(o[q], P.c_h16[coff + q], P.c_l16[coff + q]);
+        } else if (P.c_lo) {
+          const float h = __uint_as_float(__float_as_uint(o[q]) & 0xffffe000u);
+          P.c_hi[coff + q] = h;
+          P.c_lo[coff + q] = o[q] - h;
+        } else {
+          P.c_hi[coff + q] = o[q];
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem, int warp, int lane, int j0, int n0, int nk, uint32_t tmem_base,
                                             uint64_t* tfull, const uint32_t* tempty_addr) {
   const int quad = warp & 3;
@@ -202,83 +279,33 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(tempty_addr[buf]) : "memory");
   }
-  // ---- park the tile: S[row][col], plus the (batch, step) of every GEMM row -----------------------------
+  // ---- park the tile: S[row][col], plus the output / residual offsets of every GEMM row ----------------------
   float* S = reinterpret_cast<float*>(smem);
-  int* rowb = reinterpret_cast<int*>(S + TC_BM * TC_SLD);
-  int* rowt = rowb + TC_BM;
+  long* rowc = reinterpret_cast<long*>(S + TC_BM * TC_SLD);
+  long* rowr = rowc + TC_BM;
 #pragma unroll
   for (int c = 0; c < EC; c += 4)
     *reinterpret_cast<float4*>(&S[row * TC_SLD + half * EC + c]) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
   if (half == 0) {  // GEMM row j <-> padded input row j*stride -> (batch, output step)
     const int j = j0 + row;
-    int b = -1, t = 0;
+    long co = -1, ro = 0;
     if (j < P.Rs) {
       const long in_row = (long)j * P.stride;
       const int bb = (int)(in_row / P.rows_in);
       const int tin = (int)(in_row - (long)bb * P.rows_in) - P.off;
-      if (bb < P.nbatch && tin >= 0 && (tin % P.stride) == 0 && tin / P.stride < P.T_out) { b = bb; t = tin / P.stride; }
+      if (bb < P.nbatch && tin >= 0 && (tin % P.stride) == 0 && tin / P.stride < P.T_out) {
+        const int t = tin / P.stride;
+        co = (long)bb * P.c_bs + (long)t * P.c_rs;
+        ro = (long)bb * P.r_bs + (long)t * P.r_rs;
+      }
     }
-    rowb[row] = b;
-    rowt[row] = t;
+    rowc[row] = co;
+    rowr[row] = ro;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
-  // ---- write out: thread -> 4 consecutive columns, consecutive threads -> consecutive columns ----------------
-  const int et = threadIdx.x - 128;
-#pragma unroll 1
-  for (int i = et; i < TC_BM * (TC_BN / 4); i += 256) {
-    const int r = i / (TC_BN / 4), c4 = (i - r * (TC_BN / 4)) * 4;
-    const int n = n0 + c4;
-    const int b = rowb[r];
-    if (b < 0 || n >= P.N) continue;
-    const int t = rowt[r];
-    const float4 sv = *reinterpret_cast<const float4*>(&S[r * TC_SLD + c4]);
-    float o[4] = {sv.x, sv.y, sv.z, sv.w};
-    const long coff = (long)b * P.c_bs + (long)t * P.c_rs + n;
-    const long roff = (long)b * P.r_bs + (long)t * P.r_rs + n;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (n + q < P.N) {
-        float x = o[q] * P.oscale;
-        if (P.bias) x += P.bias[n + q];
-        if (P.r_hi) x += P.r_lo ? (P.r_hi[roff + q] + P.r_lo[roff + q]) : P.r_hi[roff + q];
-        o[q] = tc_act(x, P.act);
-      }
-    }
-    if (P.c_h16) {
-      if (P.c_hi)
-        for (int q = 0; q < 4 && n + q < P.N; ++q) P.c_hi[coff + q] = o[q];
-      if (n + 3 < P.N) {
-        ushort4 h, l;
-        split16(o[0], h.x, l.x); split16(o[1], h.y, l.y); split16(o[2], h.z, l.z); split16(o[3], h.w, l.w);
-        *reinterpret_cast<ushort4*>(P.c_h16 + coff) = h;
-        *reinterpret_cast<ushort4*>(P.c_l16 + coff) = l;
-      } else {
-        for (int q = 0; q < 4 && n + q < P.N; ++q) split16(o[q], P.c_h16[coff + q], P.c_l16[coff + q]);
-      }
-    } else if (n + 3 < P.N) {
-      if (P.c_lo) {
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
-        h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
-        h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
-        h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
-        *reinterpret_cast<float4*>(P.c_hi + coff) = h;
-        *reinterpret_cast<float4*>(P.c_lo + coff) = l;
-      } else {
-        *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    } else {
-      for (int q = 0; q < 4 && n + q < P.N; ++q) {
-        if (P.c_lo) {
-          const float h = __uint_as_float(__float_as_uint(o[q]) & 0xffffe000u);
-          P.c_hi[coff + q] = h;
-          P.c_lo[coff + q] = o[q] - h;
-        } else {
-          P.c_hi[coff + q] = o[q];
-        }
-      }
-    }
-  }
+  if (P.act == ACT_NONE) tc_writeout<ACT_NONE>(P, S, rowc, rowr, n0);
+  else if (P.act == ACT_GELU) tc_writeout<ACT_GELU>(P, S, rowc, rowr, n0);
+  else tc_writeout<-1>(P, S, rowc, rowr, n0);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
