@@ -223,8 +223,10 @@ __global__ void id_cols_kernel(const float* __restrict__ idv, const float* __res
     v[threadIdx.x] = a;
   }
   __syncthreads();
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < x.T * 64; i += gridDim.x * blockDim.x)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < x.T * 64; i += gridDim.x * blockDim.x) {
     x.row(b, i / 64)[off + (i & 63)] = v[i & 63];
+    if (x.h16) split16(v[i & 63], x.row_h16(b, i / 64)[off + (i & 63)], x.row_l16(b, i / 64)[off + (i & 63)]);
+  }
 }
 
 // multi-head self-attention, eager softmax(QK^T * scale) V, head_dim 64.  qkv rows are
@@ -1307,7 +1309,8 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
     ln_pre(e, t1, nullptr, L.ln2_g, L.ln2_b, hcur, nullptr, ACT_NONE, s);
   }
   // ---- audio_feature_map + id_mlp concat -> first_net -------------------------------------------------
-  Act3 cat = new_act(e, B, frame, 320, 1, s);
+  const bool tcf = tc && e->tc_f16;                       // first_net / decoder convs on the tensor-core kernel too (fp16 planes)
+  Act3 cat = new_act(e, B, frame, 320, 1, s, tcf);
   linear(e, F.feat_map, hcur, cat, ACT_NONE, nullptr, s, 0);
   if (!e->ws.sizing) {
     id_cols_kernel<<<dim3(cdiv(frame * 64, 256), B), 256, 0, s>>>(idv, F.id_w, F.id_b, F.ncls, cat, 256);
@@ -1315,13 +1318,13 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
     TS_CUDA(cudaGetLastError());
   }
   Act3 c0 = new_act(e, B, frame, 256, 0, s), r0 = new_act(e, B, frame, 256, 0, s);
-  conv1d(e, F.fn_conv[0], cat, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
-  conv1d(e, F.fn_res0, cat, 3, 1, 1, r0, frame, ACT_NONE, nullptr, s);
-  Act3 f = new_act(e, B, frame, 256, 1, s);
+  conv_auto(e, F.fn_conv[0], cat, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
+  conv_auto(e, F.fn_res0, cat, 3, 1, 1, r0, frame, ACT_NONE, nullptr, s);
+  Act3 f = new_act(e, B, frame, 256, 1, s, tcf);
   ln_pre(e, c0, nullptr, F.fn_g[0], F.fn_b[0], f, &r0, ACT_RELU, s);       // relu(LN(conv(x)) + conv_res(x))
   for (int i = 1; i < 3; ++i) {
-    conv1d(e, F.fn_conv[i], f, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
-    Act3 g = new_act(e, B, frame, 256, 1, s);
+    conv_auto(e, F.fn_conv[i], f, 3, 1, 1, c0, frame, ACT_NONE, nullptr, s);
+    Act3 g = new_act(e, B, frame, 256, 1, s, tcf);
     ln_pre(e, c0, nullptr, F.fn_g[i], F.fn_b[i], g, &f, ACT_RELU, s);      // relu(LN(conv(x)) + x)
     f = g;
   }
@@ -1333,8 +1336,8 @@ static void face_run(ts_engine* e, const float* wave, const float* idv, float* o
     Act3 m = f;
     for (int i = 0; i < 3; ++i) {
       Act3 cc = new_act(e, B, frame, c, 0, s);
-      conv1d(e, F.dec_conv[br][i], m, 3, 1, 1, cc, frame, ACT_NONE, nullptr, s);
-      Act3 nn = new_act(e, B, frame, c, 1, s);
+      conv_auto(e, F.dec_conv[br][i], m, 3, 1, 1, cc, frame, ACT_NONE, nullptr, s);
+      Act3 nn = new_act(e, B, frame, c, 1, s, tcf);
       ln_pre(e, cc, nullptr, F.dec_g[br][i], F.dec_b[br][i], nn, nullptr, ACT_RELU, s);
       m = nn;
     }

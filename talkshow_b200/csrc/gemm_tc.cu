@@ -180,10 +180,11 @@ constexpr int TC_SLD = TC_BN + 4;   // padded row of the parked tile (floats)
 // Write-out of the parked tile.  Thread -> 4 fixed columns (bias loaded once), rows strided by 4; the first version did the
 // row / column arithmetic, a runtime activation switch and scalar tails per element: ~420 instructions per float4, 28 us
 // per tile -- more than a K = 768 tile's whole main loop (ncu, profiles/r02_gemm_f16_ncu_summary.md).
-template <int ACT>
+// CG = float4 column groups per parked row (the 256 epilogue threads cover 256 / CG rows per pass), SLD = parked row stride.
+template <int ACT, int CG, int SLD>
 __device__ __forceinline__ void tc_writeout(const TcArgs& P, const float* S, const long* rowc, const long* rowr, int n0) {
   const int et = threadIdx.x - 128;
-  const int c4 = (et & 63) * 4, n = n0 + c4;
+  const int c4 = (et % CG) * 4, n = n0 + c4;
   if (n >= P.N) return;
   const int nv = min(4, P.N - n);                   // valid columns of this thread (4 except at a ragged N edge)
   float bv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -193,10 +194,10 @@ __device__ __forceinline__ void tc_writeout(const TcArgs& P, const float* S, con
   const bool rvec = nv == 4 && P.r_hi && (((P.r_bs | P.r_rs) & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.r_hi) & 15) == 0) &&
                     (!P.r_lo || (reinterpret_cast<uintptr_t>(P.r_lo) & 15) == 0);
 #pragma unroll 4
-  for (int r = et >> 6; r < TC_BM; r += 4) {
+  for (int r = et / CG; r < TC_BM; r += 256 / CG) {
     const long co = rowc[r];
     if (co < 0) continue;
-    const float4 sv = *reinterpret_cast<const float4*>(&S[r * TC_SLD + c4]);
+    const float4 sv = *reinterpret_cast<const float4*>(&S[r * SLD + c4]);
     float o[4] = {sv.x * osc + bv[0], sv.y * osc + bv[1], sv.z * osc + bv[2], sv.w * osc + bv[3]};
     if (P.r_hi) {
       const long roff = rowr[r] + n;
@@ -303,9 +304,9 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& P, unsigned char* smem
     rowr[row] = ro;
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
-  if (P.act == ACT_NONE) tc_writeout<ACT_NONE>(P, S, rowc, rowr, n0);
-  else if (P.act == ACT_GELU) tc_writeout<ACT_GELU>(P, S, rowc, rowr, n0);
-  else tc_writeout<-1>(P, S, rowc, rowr, n0);
+  if (P.act == ACT_NONE) tc_writeout<ACT_NONE, TC_BN / 4, TC_SLD>(P, S, rowc, rowr, n0);
+  else if (P.act == ACT_GELU) tc_writeout<ACT_GELU, TC_BN / 4, TC_SLD>(P, S, rowc, rowr, n0);
+  else tc_writeout<-1, TC_BN / 4, TC_SLD>(P, S, rowc, rowr, n0);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -629,6 +630,292 @@ tc2_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant
   }
 }
 
+// ---- persistent CTA-pair variant ------------------------------------------------------------------------
+// One CTA pair per TPC loops over the 256 x 256 tiles (tile = pair + i * pairs, N tiles fastest).  The roles keep running
+// counters (k-blocks for the operand ring, chunks for the two TMEM buffers), so the TMA producer and the MMA issuer run
+// straight into the next tile while the epilogue warps of both CTAs are still writing the previous one out: the write-out
+// (8 - 10 us per tile, as long as a K = 768 main loop) is hidden instead of serialised, and barrier init / TMEM allocation /
+// pipeline fill are paid once per CTA instead of once per tile.  The parked tile can no longer borrow the operand ring, so
+// every epilogue warp transposes its 32 rows x 128 columns through a private 32 x 16 park, 16 columns at a time.
+constexpr int TP_COLS = 16;                          // columns per write-out step of one warp
+constexpr int TP_SLD = TP_COLS + 4;                  // parked row stride (floats): the row-per-lane STS.128 is conflict-free
+constexpr int TP_PARK = TC_EPI_WARPS * 32 * TP_SLD * 4;   // 20 KB: a private 32 x 16 park per epilogue warp
+constexpr int TP_ROWS = TC_EPI_WARPS * 32 * 2 * 8;   // per-warp output / residual row offsets
+constexpr int TP_SMEM = T2_STAGES * T2_STAGE_BYTES + TP_PARK + TP_ROWS + 256 + 1024;
+
+// One write-out step of one epilogue warp: its 32 rows x 16 columns, parked row-per-lane, leave as 8 rows x 64 B per store
+// instruction (lane -> row lane / 4 + 8 i, 4 columns lane % 4).  Warp-private: no block barrier, the 8 warps of a CTA
+// interleave freely and hide each other's load latency.
+template <int ACT>
+__device__ __forceinline__ void tp_rows(const TcArgs& P, const float* Sw, const long* rc, const long* rr, int n, int lane) {
+  const int cg = lane & 3;
+  n += cg * 4;
+  if (n >= P.N) return;
+  const int nv = min(4, P.N - n);
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (P.bias)
+    for (int q = 0; q < nv; ++q) bv[q] = P.bias[n + q];
+  const float osc = P.oscale;
+  const bool rvec = nv == 4 && P.r_hi && (((P.r_bs | P.r_rs) & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.r_hi) & 15) == 0) &&
+                    (!P.r_lo || (reinterpret_cast<uintptr_t>(P.r_lo) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    const long co = rc[r];
+    if (co < 0) continue;
+    const float4 sv = *reinterpret_cast<const float4*>(&Sw[r * TP_SLD + cg * 4]);
+    float o[4] = {sv.x * osc + bv[0], sv.y * osc + bv[1], sv.z * osc + bv[2], sv.w * osc + bv[3]};
+    if (P.r_hi) {
+      const long roff = rr[r] + n;
+      if (rvec) {
+        const float4 rh = *reinterpret_cast<const float4*>(P.r_hi + roff);
+        if (P.r_lo) {
+          const float4 rl = *reinterpret_cast<const float4*>(P.r_lo + roff);
+          o[0] += rh.x + rl.x; o[1] += rh.y + rl.y; o[2] += rh.z + rl.z; o[3] += rh.w + rl.w;
+        } else {
+          o[0] += rh.x; o[1] += rh.y; o[2] += rh.z; o[3] += rh.w;
+        }
+      } else {
+        for (int q = 0; q < nv; ++q) o[q] += P.r_lo ? (P.r_hi[roff + q] + P.r_lo[roff + q]) : P.r_hi[roff + q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ACT == ACT_GELU) o[q] = 0.5f * o[q] * (1.0f + erff(o[q] * 0.70710678118654752440f));
+      else if (ACT != ACT_NONE) o[q] = tc_act(o[q], P.act);
+    }
+    const long coff = co + n;
+    if (nv == 4) {
+      if (P.c_h16) {
+        if (P.c_hi) *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
+        ushort4 h, l;
+        split16(o[0], h.x, l.x); split16(o[1], h.y, l.y); split16(o[2], h.z, l.z); split16(o[3], h.w, l.w);
+        *reinterpret_cast<ushort4*>(P.c_h16 + coff) = h;
+        *reinterpret_cast<ushort4*>(P.c_l16 + coff) = l;
+      } else if (P.c_lo) {
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(o[0]) & 0xffffe000u); l.x = o[0] - h.x;
+        h.y = __uint_as_float(__float_as_uint(o[1]) & 0xffffe000u); l.y = o[1] - h.y;
+        h.z = __uint_as_float(__float_as_uint(o[2]) & 0xffffe000u); l.z = o[2] - h.z;
+        h.w = __uint_as_float(__float_as_uint(o[3]) & 0xffffe000u); l.w = o[3] - h.w;
+        *reinterpret_cast<float4*>(P.c_hi + coff) = h;
+        *reinterpret_cast<float4*>(P.c_lo + coff) = l;
+      } else {
+        *reinterpret_cast<float4*>(P.c_hi + coff) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      for (int q = 0; q < nv; ++q) {
+        if (P.c_h16) {
+          if (P.c_hi) P.c_hi[coff + q] = o[q];
+          split16(o[q], P.c_h16[coff + q], P.c_l16[coff + q]);
+        } else if (P.c_lo) {
+          const float h = __uint_as_float(__float_as_uint(o[q]) & 0xffffe000u);
+          P.c_hi[coff + q] = h;
+          P.c_lo[coff + q] = o[q] - h;
+        } else {
+          P.c_hi[coff + q] = o[q];
+        }
+      }
+    }
+  }
+}
+// All 8 steps of one tile for one warp.  The step loop is NOT unrolled (the body with erff must exist once per activation);
+// the accumulator registers need constant indices, so the 16 values of step j are picked by a switch.  No function call and
+// no address of P taken: a first version passed P to a __noinline__ helper, which moved the whole argument block to local
+// memory -- with 222 KB of the SM's 228 KB given to shared memory those loads missed L1 in every role's inner loop and
+// the kernel ran 40 % slower than the one-tile-per-CTA kernel.
+template <int ACT>
+__device__ __forceinline__ void tp_tile(const TcArgs& P, const float (&acc)[TC_BN / 2], float* Sw, const long* rc, const long* rr, int nbase,
+                                        int lane) {
+#pragma unroll 1
+  for (int j = 0; j < (TC_BN / 2) / TP_COLS; ++j) {
+    float q[TP_COLS];
+    switch (j) {
+#define TP_PICK(J)                                                  \
+  case J:                                                           \
+    _Pragma("unroll") for (int c = 0; c < TP_COLS; ++c) q[c] = acc[J * TP_COLS + c]; \
+    break;
+      TP_PICK(0) TP_PICK(1) TP_PICK(2) TP_PICK(3) TP_PICK(4) TP_PICK(5) TP_PICK(6)
+      default:
+#pragma unroll
+        for (int c = 0; c < TP_COLS; ++c) q[c] = acc[7 * TP_COLS + c];
+        break;
+#undef TP_PICK
+    }
+#pragma unroll
+    for (int c = 0; c < TP_COLS; c += 4) *reinterpret_cast<float4*>(&Sw[lane * TP_SLD + c]) = make_float4(q[c], q[c + 1], q[c + 2], q[c + 3]);
+    __syncwarp();
+    tp_rows<ACT>(P, Sw, rc, rr, nbase + j * TP_COLS, lane);
+    __syncwarp();
+  }
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc2p_gemm_kernel(const __grid_constant__ CUtensorMap mA_hi, const __grid_constant__ CUtensorMap mA_lo,
+                 const __grid_constant__ CUtensorMap mB_hi, const __grid_constant__ CUtensorMap mB_lo, TcArgs P, int ntiles) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  float* S = reinterpret_cast<float*>(smem + T2_STAGES * T2_STAGE_BYTES);
+  long* rows = reinterpret_cast<long*>(smem + T2_STAGES * T2_STAGE_BYTES + TP_PARK);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + T2_STAGES * T2_STAGE_BYTES + TP_PARK + TP_ROWS);
+  uint64_t* empty = full + T2_STAGES;
+  uint64_t* tfull = empty + T2_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nk = P.taps * P.cblocks;
+  constexpr int BK = F16 ? 2 * TC_BK : TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < T2_STAGES; ++i) { mb_init(&full[i], 1); mb_init(&empty[i], 1); }
+    mb_init(&tfull[0], 1); mb_init(&tfull[1], 1);
+    mb_init(&tempty[0], 2 * TC_EPI_WARPS); mb_init(&tempty[1], 2 * TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mB_lo) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "n"(2 * TC_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      uint32_t it = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        const int nt = tile % P.cn, mp = tile / P.cn;
+        const int j0 = (2 * mp + (int)rank) * TC_BM, n0 = nt * TC_BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int st = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
+          mb_wait(&empty[st], ph ^ 1);
+          const int tap = kb / P.cblocks, cb = kb - tap * P.cblocks;
+          unsigned char* base = smem + st * T2_STAGE_BYTES;
+          const int c0 = cb * BK, c1 = tap % P.stride, c2 = j0 + tap / P.stride;
+          const int kcol = tap * P.C + cb * BK, nrow = n0 + (int)rank * (TC_BN / 2);
+          if (rank == 0) mb_expect(&full[st], 2 * T2_STAGE_BYTES);
+          const uint32_t lbar = s_u32(&full[st]) & 0xFEFFFFFFu;
+          tma_3d_2sm(base, &mA_hi, c0, c1, c2, lbar);
+          tma_3d_2sm(base + TC_A_BYTES, &mA_lo, c0, c1, c2, lbar);
+          tma_2d_2sm(base + 2 * TC_A_BYTES, &mB_hi, kcol, nrow, lbar);
+          tma_2d_2sm(base + 2 * TC_A_BYTES + T2_BHALF, &mB_lo, kcol, nrow, lbar);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ===== MMA issuer: leader CTA only =====
+      const uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      uint32_t it = 0, gch = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        int kin = 0;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int st = it % T2_STAGES, ph = (it / T2_STAGES) & 1;
+          const uint32_t buf = gch & 1;
+          if (kin == 0) {
+            mb_wait(&tempty[buf], ((gch >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          mb_wait(&full[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = s_u32(smem + st * T2_STAGE_BYTES), a_lo = a_hi + TC_A_BYTES, b_hi = a_hi + 2 * TC_A_BYTES, b_lo = b_hi + T2_BHALF;
+          const uint32_t d = tmem_base + buf * TC_BN;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint32_t o = k * 32;
+            if constexpr (F16) {
+              umma2_f16(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+              umma2_f16(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+              umma2_f16(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+            } else {
+              umma2_tf32(d, umma_desc(a_lo + o), umma_desc(b_hi + o), idesc, (kin | k) != 0);
+              umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_lo + o), idesc, 1);
+              umma2_tf32(d, umma_desc(a_hi + o), umma_desc(b_hi + o), idesc, 1);
+            }
+          }
+          umma2_commit(&empty[st]);
+          if (++kin == P.chunk || kb == nk - 1) {
+            umma2_commit(&tfull[buf]);
+            ++gch;
+            kin = 0;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {  // ===== epilogue warps of both CTAs =====
+    uint32_t te[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(te[i]) : "r"(s_u32(&tempty[i])), "r"(0));
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int nchunks = (nk + P.chunk - 1) / P.chunk;
+    float* Sw = S + (warp - 4) * (32 * TP_SLD);          // this warp's park
+    long* rc = rows + (warp - 4) * 64;                   // its rows' output offsets (-1: discarded) and residual offsets
+    long* rr = rc + 32;
+    constexpr int EC = TC_BN / 2;                        // 128 columns per warp: [half * 128, +128)
+    uint32_t gch = 0;
+    for (int tile = pair; tile < ntiles; tile += npairs) {
+      const int nt = tile % P.cn, mp = tile / P.cn;
+      const int j0 = (2 * mp + (int)rank) * TC_BM, n0 = nt * TC_BN;
+      float acc[EC];
+#pragma unroll
+      for (int i = 0; i < EC; ++i) acc[i] = 0.f;
+      for (int c = 0; c < nchunks; ++c, ++gch) {
+        const uint32_t buf = gch & 1;
+        mb_wait(&tfull[buf], (gch >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int cc = 0; cc < EC / 16; ++cc) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * TC_BN + half * EC + cc * 16, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[cc * 16 + i] += __uint_as_float(v[i]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(te[buf]) : "memory");
+      }
+      {  // GEMM row j <-> padded input row j*stride -> (batch, output step)
+        const int j = j0 + row;
+        long co = -1, ro = 0;
+        if (j < P.Rs) {
+          const long in_row = (long)j * P.stride;
+          const int bb = (int)(in_row / P.rows_in);
+          const int tin = (int)(in_row - (long)bb * P.rows_in) - P.off;
+          if (bb < P.nbatch && tin >= 0 && (tin % P.stride) == 0 && tin / P.stride < P.T_out) {
+            const int t = tin / P.stride;
+            co = (long)bb * P.c_bs + (long)t * P.c_rs;
+            ro = (long)bb * P.r_bs + (long)t * P.r_rs;
+          }
+        }
+        rc[lane] = co;
+        rr[lane] = ro;
+      }
+      __syncwarp();
+      if (P.act == ACT_NONE) tp_tile<ACT_NONE>(P, acc, Sw, rc, rr, n0 + half * EC, lane);
+      else if (P.act == ACT_GELU) tp_tile<ACT_GELU>(P, acc, Sw, rc, rr, n0 + half * EC, lane);
+      else tp_tile<-1>(P, acc, Sw, rc, rr, n0 + half * EC, lane);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TC_BN) : "memory");
+  }
+}
+
 // ---- split kernels ------------------------------------------------------------------------------
 __global__ void split_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long n) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -781,22 +1068,32 @@ void tc_conv1d(ts_engine* e, const Layer& L, const Act3& x, int k, int stride, i
     TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
     TS_CUDA(cudaFuncSetAttribute(tc2_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2p_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
+    TS_CUDA(cudaFuncSetAttribute(tc2p_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM));
     e->tc_attr_set = true;
   }
   // grid padded to whole clusters; surplus tiles fall outside Rs / N and are masked (TMA zero-fills OOB)
   dim3 grid((unsigned)(((tiles_n + cn - 1) / cn) * cn), (unsigned)(((tiles_m + cm - 1) / cm) * cm));
   if (pair) grid = dim3((unsigned)(2 * tiles_n * ((tiles_m + 1) / 2)), 1, 1);
+  static const bool persist_env = !(getenv("TS_TC_PERSIST") && getenv("TS_TC_PERSIST")[0] == '0');
+  const int ntiles = tiles_n * ((tiles_m + 1) / 2);
+  // persistent CTA pairs (one per TPC) looping over the tiles -- when every pair gets at least two tiles; below that there is
+  // nothing to overlap and the block-wide write-out of the one-tile kernel is the faster one (face, 8 clips: 5.7 vs 5.9 ms)
+  const bool persist = pair && !onchip && persist_env && ntiles >= 2 * std::max(1, e->sm_count / 2);
+  if (persist) grid = dim3((unsigned)(2 * std::min(ntiles, std::max(1, e->sm_count / 2))), 1, 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = pair ? T2_SMEM : TC_SMEM;
+  cfg.dynamicSmemBytes = persist ? TP_SMEM : pair ? T2_SMEM : TC_SMEM;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = pair ? 2 : cn; at[0].val.clusterDim.y = pair ? 1 : cm; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (f16) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false, true>, mAh, mAl, mBh, mBl, P));
+  if (persist && f16) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2p_gemm_kernel<true>, mAh, mAl, mBh, mBl, P, ntiles));
+  else if (persist) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2p_gemm_kernel<false>, mAh, mAl, mBh, mBl, P, ntiles));
+  else if (f16) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false, true>, mAh, mAl, mBh, mBl, P));
   else if (pair && onchip) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<true, false>, mAh, mAl, mBh, mBl, P));
   else if (pair) TS_CUDA(cudaLaunchKernelEx(&cfg, tc2_gemm_kernel<false, false>, mAh, mAl, mBh, mBl, P));
   else TS_CUDA(cudaLaunchKernelEx(&cfg, tc_gemm_kernel, mAh, mAl, mBh, mBl, P));

@@ -30,13 +30,14 @@ class WholeBody:
     persistent CTAs launched as CTA pairs (whole TPCs), and the face kernels fill the remaining TPCs.  Results are
     bit-identical to the sequential order (same kernels, same arithmetic)."""
 
-    def __init__(self, engine: Engine, overlap_batch=8, overlap_ctas=100):
+    def __init__(self, engine: Engine, overlap_batch=32, overlap_ctas=96):
         self.e = engine
         self.device = engine.device
         self.overlap_batch = overlap_batch if not getattr(engine, "host_only", True) else 0
         self.overlap_ctas = overlap_ctas
         self.e2 = None            # body path engine with the partial-GPU sampler plan (same device)
         self._side = None
+        self._body_engine = engine   # the engine whose sampler ran in the last generate()
 
     def load(self, pixel_ckpt, vq_ckpt, face_ckpt):
         """Checkpoint dicts in the reference's formats (talkshow_b200/synth.py docstring)."""
@@ -55,6 +56,10 @@ class WholeBody:
             self.e2.load_vq(0, vq_ckpt["g_body"])
             self.e2.load_vq(1, vq_ckpt["g_hand"])
             self._side = torch.cuda.Stream(device=self.device)
+
+    def pixelcnn_last_ms(self):
+        """Device time of the sampler launch of the last ``generate`` (events on its launch stream, inside the library)."""
+        return self._body_engine.pixelcnn_last_ms()
 
     def close(self):
         if self.e2 is not None:
@@ -75,6 +80,7 @@ class WholeBody:
             # small batch: sampler (on overlap_ctas SMs, launched first) and face regressor (on the free TPCs) side by side
             cur = torch.cuda.current_stream(self.device)
             self._side.wait_stream(cur)
+            self._body_engine = self.e2
             with torch.cuda.stream(self._side):
                 _, body = self.e2.body_generate(mfcc, label, noise, want_codes=False)
             face = self.e.face_forward(wave, idz, frame)
@@ -84,6 +90,7 @@ class WholeBody:
                 if torch.is_tensor(t) and t.is_cuda:
                     t.record_stream(self._side)                          # allocated here, consumed on the side stream
             return self.e.assemble_pose(face, body, stand)
+        self._body_engine = self.e
         face = self.e.face_forward(wave, idz, frame)
         _, body = self.e.body_generate(mfcc, label, noise, want_codes=False)
         return self.e.assemble_pose(face, body, stand)
