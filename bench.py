@@ -227,7 +227,7 @@ def run_ours(args, rank, world, local_rank):
     eng = Engine(local_rank)
     if world > 1:
         eng.nccl_init(rank, world)                    # the pose all-gather runs inside the library (ts_allgather)
-    wb = WholeBody(eng, overlap_batch=int(os.environ.get("TS_OVERLAP_BATCH", "32")), overlap_ctas=int(os.environ.get("TS_OVERLAP_CTAS", "96")))
+    wb = WholeBody(eng, overlap_batch=int(os.environ.get("TS_OVERLAP_BATCH", "64")), overlap_ctas=int(os.environ.get("TS_OVERLAP_CTAS", "96")))
     ck = synthetic_ckpts()
     wb.load(ck["pixel"], ck["vq"], ck["face"])
 
@@ -314,21 +314,32 @@ def run_ours(args, rank, world, local_rank):
     strong = args.scaling == "strong"
     Bg = args.batch if strong else args.batch * world
     main = Workload(Bg, args.seconds, 1234, sliced_noise=strong)
-    eng.pixelcnn_timing(True)
+    wb.pixelcnn_timing(True)
     with ClockSampler(local_rank) as clk:
         for _ in range(args.warmup):
             main.step_device()
-        l0 = eng.launches
+        l0 = wb.launches
         torch.manual_seed(2024)
         dev_ms, _ = timed(main.step_device, args.steps)
-        l1 = eng.launches
-        pix_ms = [wb.pixelcnn_last_ms()]
+        l1 = wb.launches
+        pix_in_step = [wb.pixelcnn_last_ms()]
         main.step_host()                               # e2e warm-up (pinned staging buffers, allocator)
         _, e2e_ms = timed(main.step_host, args.steps)
-    # a few more timed sampler launches for the roofline average (events on its launch stream, inside the library)
+    # a few more timed sampler launches (events on its launch stream, inside the library): in the step as it runs (side by
+    # side with the face path when the batch is overlapped) ...
     for _ in range(3):
         main.step_device()
-        pix_ms.append(wb.pixelcnn_last_ms())
+        pix_in_step.append(wb.pixelcnn_last_ms())
+    pix_in_step = [x for x in pix_in_step if x > 0]
+    pix_step_avg = sum(pix_in_step) / max(1, len(pix_in_step))
+    # ... and ALONE on the whole GPU (sequential order, every SM): the roofline figure of the kernel itself
+    ob, wb.overlap_batch = wb.overlap_batch, 0
+    pix_ms = []
+    for i in range(4):
+        main.step_device()
+        if i:
+            pix_ms.append(wb.pixelcnn_last_ms())
+    wb.overlap_batch = ob
     pix_ms = [x for x in pix_ms if x > 0]
     pix_avg = sum(pix_ms) / max(1, len(pix_ms))
     # dense-contraction side of the step: the face regressor alone (wav2vec2 CNN + transformer; tcgen05 3xTF32)
@@ -361,14 +372,14 @@ def run_ours(args, rank, world, local_rank):
     tile = 16 if main.b <= 16 else 32 if main.b <= 32 else 64
     overlapped = wb.e2 is not None and 0 < main.b <= wb.overlap_batch
     roofline = {"kernel": "pixelcnn_kernel<persistent, batch tile %d> (gated-PixelCNN sampler, fused 52-stage plan, %d rows/launch, "
-                          "%d samples on this GPU%s)" % (tile, T, main.b, ", on %d of the %d SMs with the face path on the others (two streams)"
-                                                         % (wb.overlap_ctas, eng.sm_count) if overlapped else ""),
+                          "%d samples on this GPU%s)" % (tile, T, main.b, "; launch_ms = alone on %d SMs, launch_ms_in_step = on %d SMs next to the "
+                                                         "face path (two streams)" % (eng.sm_count, wb.overlap_ctas) if overlapped else ""),
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "traffic": NCU_DRAM_BYTES_PER_ROW[tile] * T, "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this "
                 "kernel per latent row (profiles/r02_pixelcnn_ncu_summary.md: 163.6 MB at the 64-sample tile, 153.0 MB at the 16-sample tile; 32: "
                 "between, not captured) x %d rows; staged bytes per launch: %d" % (T, eng.pixelcnn_staged_row_bytes * T), "launch_ms": pix_avg,
-                "algorithmic_bytes": alg_bytes, "share_of_step": pix_avg / (dev_ms / args.steps)}
+                "launch_ms_in_step": pix_step_avg, "algorithmic_bytes": alg_bytes, "share_of_step": pix_step_avg / (dev_ms / args.steps)}
     # 106 GFLOP per 10 s clip (53 GMAC), scaled with the clip length
     face_flop = 106.0e9 * main.b * args.seconds / 10.0
     # fp32-grade MACs as three kind::f16 products on fp16-split operands (the default since r02; 3xTF32 would be bf16/2/3)
@@ -411,7 +422,7 @@ def run_ours(args, rank, world, local_rank):
         alg3 = eng.pixelcnn_row_bytes * c3.T
         line["config3"] = dict(r3, unit="frames/s", workload="BASELINE config 3: 1 clip x 4 s, id 0 (runs on rank 0's GPU)",
                                roofline={"bound": "hbm", "launch_ms": pix3, "frac": (alg3 / (pix3 * 1e-3) / 1e9 / hbm_peak) if pix3 > 0 else None})
-    eng.pixelcnn_timing(False)
+    wb.pixelcnn_timing(False)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.stderr.write("[bench] device legs done: value %.0f frames/s, e2e %.0f frames/s; timing the CPU arm sample\n" % (value, e2e_val))
         frames, ts = time_cpu(ck, args.cpu_clips, args.seconds, 1, 0)
