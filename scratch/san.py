@@ -31,3 +31,13 @@ if what in ("all", "lbs"):
     print("lbs", float(v.abs().max()), tuple(j.shape))
 e.close()
 print("done")
+
+if what in ("all", "wb"):
+    from talkshow_b200.pipeline import WholeBody
+    e3 = Engine(0)
+    w = WholeBody(e3)                       # overlapped: sampler on a 96-CTA plan (second engine, side stream) next to the face path
+    w.load(ck, vq, synth.face_checkpoint(0))
+    out = w.generate(synth.synth_mfcc(2, 12, seed=5).cuda(), synth.synth_wave(2, 16000, seed=6).cuda(), torch.tensor([1, 3]).cuda())
+    torch.cuda.synchronize()
+    print("whole body (overlapped)", tuple(out.shape), float(out.abs().max()))
+    w.close(); e3.close()
