@@ -160,14 +160,18 @@ double ts_pixelcnn_last_ms(ts_engine* e);
  * can interpret it on the CPU; sizes are returned when the buffers are NULL. */
 int ts_debug_pixelcnn_plan(ts_engine* e, int32_t* table, int64_t* table_len, float* blob, int64_t* blob_len);
 /* dense C[M,N] = act(A[M,K] W[N,K]^T + bias) through one of the two GEMM kernels (unit tests):
- * mode 0 = fp32 FFMA kernel, mode 1 = tcgen05 3xTF32 tensor-core kernel (K % 32 == 0). */
+ * mode 0 = fp32 FFMA kernel, 1 = tcgen05 3xTF32 kernel (K % 32 == 0), 2 = on-chip split (needs ts_set_tensor_cores(e, 5)),
+ * 3 = tcgen05 fp16-split kernel (K % 64 == 0). */
 int ts_debug_gemm(ts_engine* e, int mode, const float* A, const float* W, const float* bias, float* C, int M, int N,
                   int K, int act, void* stream);
-/* Dense-contraction kernel selection (default covered by the GPU tests; the others by scratch/ab_tc.py):
- * 1 (default) / 3: tcgen05 3xTF32 kernel, CTA pair (cta_group::2) 256x256 tile;
- * 4: tcgen05 3xTF32 kernel, single CTA 128x256 tile; 2: same in clusters with TMA multicast of the operand boxes;
- * 5: CTA-pair kernel on plain operands, hi / lo split in shared memory by converter warps (bit-identical, measured slower);
- * 0: everything on the fp32 FFMA kernel. */
+/* Dense-contraction kernel for the face network and the VQ decoder (csrc/gemm_tc.cu):
+ *   6 (default) tcgen05 CTA-pair kernel (cta_group::2, 256x256 tile) on two-term fp16-split operands (kind::f16, three
+ *       products per MAC: fp32-grade results at twice the tf32 rate; operands must stay below 65504 in magnitude -- weights are
+ *       pre-scaled per layer),
+ *   1 / 3 the same kernel on 3xTF32 operands pre-split in HBM by the producing epilogue (full fp32 range),
+ *   5 experiment: plain fp32 operands, tf32 hi / lo split by converter warps in shared memory (measured slower),
+ *   4 single-CTA 128x256 kernel (tf32), 2 the same in clusters with TMA multicast, 0 everything on the fp32 FFMA2 kernel.
+ * Every mode keeps the face outputs within 1e-4 of the reference (tests/test_gpu_parity.py). */
 int ts_set_tensor_cores(ts_engine* e, int enable);
 /* PixelCNN executor: 0 (default) = grid-wide persistent cooperative kernel (grid barrier; batch tile 16 / 32 / 64 picked per
  * launch), 1 = the same device code, one launch per stage (debug cross-check), 2 = cluster-resident executor: 16-CTA
@@ -186,7 +190,7 @@ int ts_pixelcnn_trace_read(ts_engine* e, uint64_t* out, int64_t* len);
 
 /* Persistent CTAs of the grid-wide plan built by the NEXT ts_load_pixelcnn (0 = one per SM).  A smaller even count (>= 64)
  * launches the sampler as CTA pairs on that many SMs and leaves the other TPCs free for kernels of another stream: with
- * 8 clips per GPU the latency-bound sampler and the face regressor run side by side (talkshow_b200/pipeline.py). */
+ * the latency-bound sampler and the face regressor run side by side (talkshow_b200/pipeline.py: 64 clips 59.2 -> 51.0 ms). */
 int ts_set_pixelcnn_ctas(ts_engine* e, int n);
 
 /* Plan built by the NEXT ts_load_pixelcnn: 1 (default) = fused 52-stage plan (adjacent linear maps of the horizontal
