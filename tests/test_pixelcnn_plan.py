@@ -11,10 +11,12 @@ from talkshow_b200 import _lib, synth
 from talkshow_b200.engine import Engine
 
 
-@pytest.fixture(scope="module", params=["fused", "plain", "sched2"])
+@pytest.fixture(scope="module", params=["fused", "plain", "sched2", "fused96"])
 def plan(ckpts, request):
     e = Engine(-148)            # host-only planning engine sized for 148 SMs
     e.set_pixelcnn_fusion({"plain": 0, "sched2": 2}.get(request.param, 1))
+    if request.param == "fused96":          # the partial-GPU plan of the two-stream step: 96 CTAs, output_conv.2 over two stages
+        e.set_pixelcnn_ctas(96)
     e.load_pixelcnn(ckpts["pixel"]["generator"])
     table, blob = _lib.plan_to_numpy(e.h)
     rb = e.pixelcnn_row_bytes
@@ -32,8 +34,9 @@ def _audio_terms(sd, aud):
 
 def test_plan_shape(plan):
     p, row_bytes = plan
-    assert p.ncta == (132 if p.cl == 4 else 148) and p.L == 15 and p.nstages in (52, 84)
-    fused = p.nstages == 52
+    assert p.ncta in (96, 148) and p.L == 15 and p.nstages in (52, 54, 84)
+    assert (p.ncta == 96) == (p.nstages == 54)          # 2048 / (16 rows x 96 CTAs) -> output_conv.2 takes two stages per column
+    fused = p.nstages in (52, 54)
     assert (p.table[:, :, 0] >= 11).any() == fused      # EPI_HRESF / EPI_HGATE2 / EPI_OUT1F only in the fused plan
     assert row_bytes == 89774080        # SURVEY.md §8d algorithmic bytes per latent row
     t = p.table
@@ -44,11 +47,12 @@ def test_plan_shape(plan):
         for epi, layer, col in {tuple(x) for x in t[s][:, :3].tolist() if x[0] not in (0, 10)}:
             sel = t[s][(t[s][:, 0] == epi) & (t[s][:, 1] == layer) & (t[s][:, 2] == col)]
             rows = sorted((int(r0), int(n)) for r0, n in sel[:, 3:5])
-            pos = 0
+            pos = rows[0][0]
+            assert pos in (0, 1024)                          # 1024: second half of a split output_conv.2
             for r0, n in rows:
                 assert r0 == pos
                 pos += n
-            assert pos in (256, 512, 2048)
+            assert pos - rows[0][0] in (256, 512, 1024, 2048)
     if p.hvslots > 2:                                       # schedule 2: no vert_to_horiz in the vertical stages 2..15
         assert not ((t[2:16, :, 0] == PE.EPI_V2H) | (t[2:16, :, 0] == PE.EPI_V2H1)).any()
         assert (t[16:, :, 0] == PE.EPI_V2H1).any()
