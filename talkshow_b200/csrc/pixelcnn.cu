@@ -30,13 +30,30 @@ struct Job {
   int rofs = 0;   // first output row of this job inside the layer's row space (output_conv.2 split over two stages)
 };
 
+constexpr double PIX_ROWCOST = 0.0;   // default per-row fixed cost of the CTA split, in units of K (TS_PIX_ROWCOST overrides)
+
+// weight rows one CTA can take in a matmul task of depth K: 16 (the accumulator tile), fewer when (K + 1) x rows would not fit
+// one staging buffer — K = 1536 (layer-0 vertical stack): 12
+static int rows_cap(int K) { return std::min(PIX_MAXROWS, (PIX_WBUF / (K + 1)) & ~3); }
+
+// layer-0 vertical stack of both columns: one stage, or one stage per column when the plan has too few CTAs for both
+// (2 x ceil(512 / 12) = 86)
+static void push_vert0(std::vector<std::vector<Job>>& st, int D, bool split) {
+  if (split) {
+    st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}});
+    st.push_back({{EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  } else {
+    st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  }
+}
+
 // Fused plan: every linear stage of the horizontal stack is folded into the gate matmul that consumes it
 // (W_next (W_res g + b + x) = (W_next W_res) g + W_next b + W_next x), the layer-0 gate of column 0 (no
 // matmul) rides in the last vertical stage, and the layer-0 gate of column 1 is a table lookup done by the
 // sampler itself: 16 + 2 x 18 = 52 dependent stages per row instead of 84.
-static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D, int out2_split = 1) {
+static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D, int out2_split = 1, bool v0_split = false) {
   std::vector<std::vector<Job>> st;
-  st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  push_vert0(st, D, v0_split);
   st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});
   for (int l = 1; l < L; ++l) {
     std::vector<Job> j = {{EPI_VERT, l, 0, 2 * D, 4 * D, 1, true}, {EPI_VERT, l, 1, 2 * D, 4 * D, 1, true}};
@@ -64,9 +81,9 @@ static std::vector<std::vector<Job>> build_stages_fused(int L, int D = PIX_D, in
 // difference being the 49 CTAs that vert_to_horiz of the previous layer occupies.  Its output is consumed only by the
 // horizontal pass of the same row, so here it runs per column (EPI_V2H1) beside the horizontal stage that precedes
 // its consumer; the pre-gate vertical outputs (HV) get one slot per layer instead of a 2-deep ring.
-static std::vector<std::vector<Job>> build_stages_fused2(int L, int D = PIX_D) {
+static std::vector<std::vector<Job>> build_stages_fused2(int L, int D = PIX_D, int out2_split = 1, bool v0_split = false) {
   std::vector<std::vector<Job>> st;
-  st.push_back({{EPI_VERT0, 0, 0, 2 * D, 6 * D, 1, true}, {EPI_VERT0, 0, 1, 2 * D, 6 * D, 1, true}});
+  push_vert0(st, D, v0_split);
   st.push_back({{EPI_FUSEV, 0, 0, D, D, 2, false}, {EPI_V2H, 0, 0, 2 * D, 2 * D, 2, false}});   // layer 0: needed by both layer-0 gates
   for (int l = 1; l < L; ++l) {
     std::vector<Job> j = {{EPI_VERT, l, 0, 2 * D, 4 * D, 1, true}, {EPI_VERT, l, 1, 2 * D, 4 * D, 1, true}};
@@ -86,7 +103,7 @@ static std::vector<std::vector<Job>> build_stages_fused2(int L, int D = PIX_D) {
       st.push_back(j);
     }
     st.push_back({{EPI_OUT1F, 0, c, 512, 2 * D, 1, false}});
-    st.push_back({{EPI_OUT2, 0, c, PIX_NCODE, 512, 1, false}});
+    for (int q = 0; q < out2_split; ++q) st.push_back({{EPI_OUT2, 0, c, PIX_NCODE / out2_split, 512, 1, false, q * (PIX_NCODE / out2_split)}});
     st.push_back({{EPI_SAMPLE, 0, c, 0, c == 0 ? 1 : 0, 1, false}});
   }
   return st;
@@ -306,8 +323,11 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
   if (P->ncta < PIX_MB) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan needs >= %d SMs (have %d)", PIX_MB, P->ncta);
   P->fused = fused;
   const int out2_split = (PIX_NCODE + PIX_MAXROWS * P->ncta - 1) / (PIX_MAXROWS * P->ncta);   // 1 for >= 128 CTAs
-  if (out2_split > 1 && P->sched != 1) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d CTAs need the fused plan", P->ncta);
-  auto stages = P->sched == 2 ? build_stages_fused2(L) : fused ? build_stages_fused(L, PIX_D, out2_split) : build_stages(L);
+  if (out2_split > 1 && !fused) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d CTAs need the fused plan", P->ncta);
+  const bool v0_split = fused && 2 * cdiv(2 * D, rows_cap(6 * D)) > P->ncta / cl;   // fewer than 86 CTAs
+  auto stages = P->sched == 2 ? build_stages_fused2(L, PIX_D, out2_split, v0_split)
+                : fused       ? build_stages_fused(L, PIX_D, out2_split, v0_split)
+                              : build_stages(L);
   P->nstages = (int)stages.size();
   if (P->nstages > 160) fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: %d stages per row (> 160)", P->nstages);
   P->table.assign((size_t)P->nstages * P->ncta, PixTask{0, 0, 0, 0, 0, 0, 0, 0});
@@ -347,14 +367,14 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
     double tot = 0;
     // cost of a job ~ rows x (K + alpha): alpha (TS_PIX_ROWCOST, default 0 = FMA count) is the per-row fixed cost in units of
     // K — the stage trace shows K = 256 tasks with 12-13 rows finishing last, i.e. rows cost more than their FMAs
-    static const double alpha = getenv("TS_PIX_ROWCOST") ? atof(getenv("TS_PIX_ROWCOST")) : 0.0;
+    const double alpha = getenv("TS_PIX_ROWCOST") ? atof(getenv("TS_PIX_ROWCOST")) : PIX_ROWCOST;   // read per plan build
     for (auto& j : jobs) { double c = (double)j.nrows * (j.K ? std::max(j.K, 256) + alpha : 16) * j.ncol; cost.push_back(c); tot += c; }
     std::vector<int> nc(jobs.size()), lo(jobs.size());
     int used = 0;
     const int nunit = P->ncta / cl;                    // work units of a stage: CTAs, or clusters of the cluster plan
     const int rowcap = PIX_MAXROWS;
     for (size_t i = 0; i < jobs.size(); ++i) {
-      const int cap = jobs[i].K ? rowcap : 4 * PIX_MAXROWS;  // matmul rows per unit; epilogue-only tasks: 64
+      const int cap = jobs[i].K ? rows_cap(jobs[i].K / cl) : 4 * PIX_MAXROWS;  // matmul rows per unit; epilogue-only tasks: 64
       lo[i] = (jobs[i].nrows + cap - 1) / cap;
       nc[i] = std::max(lo[i], (int)std::floor(nunit * cost[i] / tot));
       used += nc[i];

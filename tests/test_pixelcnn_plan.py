@@ -11,12 +11,20 @@ from talkshow_b200 import _lib, synth
 from talkshow_b200.engine import Engine
 
 
-@pytest.fixture(scope="module", params=["fused", "plain", "sched2", "fused96"])
+# name -> (fusion level, persistent CTAs or 0 = one per SM).  fused96: the partial-GPU plan of the two-stream step (output_conv.2
+# over two stages); sched2_*: schedule 2 on partial-GPU plans (88: + output_conv.2 split; 80: + layer-0 vertical stack one column
+# per stage, 55 stages)
+PLANS = {"fused": (1, 0), "plain": (0, 0), "sched2": (2, 0), "fused96": (1, 96), "sched2_96": (2, 96), "sched2_88": (2, 88),
+         "sched2_80": (2, 80)}
+
+
+@pytest.fixture(scope="module", params=list(PLANS))
 def plan(ckpts, request):
     e = Engine(-148)            # host-only planning engine sized for 148 SMs
-    e.set_pixelcnn_fusion({"plain": 0, "sched2": 2}.get(request.param, 1))
-    if request.param == "fused96":          # the partial-GPU plan of the two-stream step: 96 CTAs, output_conv.2 over two stages
-        e.set_pixelcnn_ctas(96)
+    level, ctas = PLANS[request.param]
+    e.set_pixelcnn_fusion(level)
+    if ctas:
+        e.set_pixelcnn_ctas(ctas)
     e.load_pixelcnn(ckpts["pixel"]["generator"])
     table, blob = _lib.plan_to_numpy(e.h)
     rb = e.pixelcnn_row_bytes
@@ -34,9 +42,11 @@ def _audio_terms(sd, aud):
 
 def test_plan_shape(plan):
     p, row_bytes = plan
-    assert p.ncta in (96, 148) and p.L == 15 and p.nstages in (52, 54, 84)
-    assert (p.ncta == 96) == (p.nstages == 54)          # 2048 / (16 rows x 96 CTAs) -> output_conv.2 takes two stages per column
-    fused = p.nstages in (52, 54)
+    assert p.ncta in (80, 88, 96, 148) and p.L == 15 and p.nstages in (52, 54, 55, 84)
+    # 2048 / (16 rows x CTAs) -> output_conv.2 takes two stages per column below 128 CTAs; below 86 CTAs the layer-0 vertical
+    # stack (K = 1536: 12 rows per CTA) takes one stage per column
+    assert p.nstages == {148: p.nstages, 96: 54, 88: 54, 80: 55}[p.ncta]
+    fused = p.nstages in (52, 54, 55)
     assert (p.table[:, :, 0] >= 11).any() == fused      # EPI_HRESF / EPI_HGATE2 / EPI_OUT1F only in the fused plan
     assert row_bytes == 89774080        # SURVEY.md §8d algorithmic bytes per latent row
     t = p.table
@@ -54,8 +64,11 @@ def test_plan_shape(plan):
                 pos += n
             assert pos - rows[0][0] in (256, 512, 1024, 2048)
     if p.hvslots > 2:                                       # schedule 2: no vert_to_horiz in the vertical stages 2..15
-        assert not ((t[2:16, :, 0] == PE.EPI_V2H) | (t[2:16, :, 0] == PE.EPI_V2H1)).any()
-        assert (t[16:, :, 0] == PE.EPI_V2H1).any()
+        vert = np.array([(t[s, :, 0] == 2).any() for s in range(p.nstages)])     # stages holding EPI_VERT tasks (layers >= 1)
+        assert vert.sum() == p.L - 1
+        assert not ((t[vert][:, :, 0] == PE.EPI_V2H) | (t[vert][:, :, 0] == PE.EPI_V2H1)).any()
+        last = int(np.nonzero(vert)[0].max())
+        assert (t[last + 1:, :, 0] == PE.EPI_V2H1).any()
 
 
 def test_plan_teacher_forced_logits(plan, ckpts):
