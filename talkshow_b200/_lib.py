@@ -68,6 +68,7 @@ SYMBOLS = {
     "ts_rot6d_to_axis_angle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ts_set_pixelcnn_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "ts_set_pixelcnn_ctas": (C.c_int, [C.c_void_p, C.c_int]),
+    "ts_set_vq_parallel": (C.c_int, [C.c_void_p, C.c_int]),
     "ts_set_tensor_cores": (C.c_int, [C.c_void_p, C.c_int]),
     "ts_debug_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                 C.c_int, C.c_int, C.c_void_p]),

@@ -58,6 +58,9 @@ extern "C" void ts_engine_destroy(ts_engine* e) {
   if (!e->host_only) {
     ts::DeviceGuard g(e);
     cudaDeviceSynchronize();
+    if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+    if (e->aux_fork) cudaEventDestroy(e->aux_fork);
+    if (e->aux_join) cudaEventDestroy(e->aux_join);
     for (void* p : e->owned) cudaFree(p);
     for (auto& kv : e->slot_mem)
       for (void* p : kv.second) cudaFree(p);
@@ -84,6 +87,12 @@ extern "C" int ts_set_pixelcnn_mode(ts_engine* e, int mode) {
 extern "C" int ts_set_pixelcnn_ctas(ts_engine* e, int n) {
   if (!e || n < 0) return TS_ERR_INVALID;
   e->pixel_ctas = n;
+  return TS_OK;
+}
+
+extern "C" int ts_set_vq_parallel(ts_engine* e, int max_batch) {
+  if (!e || max_batch < 0) return TS_ERR_INVALID;
+  e->vq_parallel_batch = max_batch;
   return TS_OK;
 }
 
@@ -215,9 +224,29 @@ extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* 
     pixelcnn_generate_act(e, a, label, noise, idx, nullptr, B, T, nullptr, 0, s);
     split_codes(e, idx, idx_c, B, T, codes, s);
     const int c0 = e->conv->vq[0].out_dim, c1 = e->conv->vq[1].out_dim;   // 39 + 90 (axis-angle) or 78 + 180 (6-D)
+    // Small batches: each decoder is a chain of ~20 launches that fill a few SMs, so the hand decoder runs on a second
+    // stream beside the body decoder (fork after the code split, join before the call returns to the caller's stream).
+    // The two chains share nothing but their input codes: separate workspace blocks, disjoint columns of `poses`.
+    const bool par = !e->ws.sizing && B <= e->vq_parallel_batch;
+    if (par) {
+      if (!e->aux_stream) {
+        int prio = 0;
+        TS_CUDA(cudaStreamGetPriority(s, &prio));      // the body path may run on a high-priority stream (pipeline.WholeBody)
+        TS_CUDA(cudaStreamCreateWithPriority(&e->aux_stream, cudaStreamNonBlocking, prio));
+        TS_CUDA(cudaEventCreateWithFlags(&e->aux_fork, cudaEventDisableTiming));
+        TS_CUDA(cudaEventCreateWithFlags(&e->aux_join, cudaEventDisableTiming));
+      }
+      TS_CUDA(cudaEventRecord(e->aux_fork, s));
+      TS_CUDA(cudaStreamWaitEvent(e->aux_stream, e->aux_fork, 0));
+    }
     for (int w = 0; w < 2; ++w) {
-      Act3 y = run_vq_decode(e, e->conv->vq[w], idx_c + (size_t)w * B * T, B, T, s);
-      act_to_btc(e, y, e->conv->vq[w].out_dim, poses, c0 + c1, w ? c0 : 0, s);
+      cudaStream_t sw = (w == 1 && par) ? e->aux_stream : s;
+      Act3 y = run_vq_decode(e, e->conv->vq[w], idx_c + (size_t)w * B * T, B, T, sw);
+      act_to_btc(e, y, e->conv->vq[w].out_dim, poses, c0 + c1, w ? c0 : 0, sw);
+    }
+    if (par) {
+      TS_CUDA(cudaEventRecord(e->aux_join, e->aux_stream));
+      TS_CUDA(cudaStreamWaitEvent(s, e->aux_join, 0));
     }
   };
   e->ws.begin_sizing();

@@ -146,6 +146,12 @@ struct ts_engine {
   void* smplx = nullptr;        // ts::SmplxModel (lbs.cu)
   void* nccl = nullptr;         // ts::NcclApi (collective.cu): dlopen'ed NCCL + this engine's communicator
   ts::Workspace ws;
+  // second stream of the fused body path (the two VQ decoders of a small batch run side by side) + its fork / join events
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+  // largest batch whose two decoders run concurrently (ts_set_vq_parallel; 0 = one after the other).  Measured on a B200
+  // (profiles/r02c_vq_decoders_side_by_side*.log): -0.6 ms per call at 1..16 samples (8-clip step 22.9 -> 22.3 ms), neutral at 32 / 64
+  int vq_parallel_batch = 16;
   std::vector<void*> owned;  // device allocations that live as long as the engine
   // allocations of the weight sets, one slot per loadable module ("pixelcnn", "audioenc", "vq0", "vq1", "face"):
   // reloading a module frees the previous set (ts::LoadScope), a failed load frees its partial uploads

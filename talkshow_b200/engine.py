@@ -99,6 +99,10 @@ class Engine:
         """Persistent CTAs of the grid-wide sampler plan built by the next load_pixelcnn (0 = one per SM)."""
         self._check(self.L.ts_set_pixelcnn_ctas(self.h, int(n)), "ts_set_pixelcnn_ctas")
 
+    def set_vq_parallel(self, max_batch):
+        """body_generate: run the two VQ decoders of batches <= max_batch side by side on two streams (0: one after the other)."""
+        self._check(self.L.ts_set_vq_parallel(self.h, int(max_batch)), "ts_set_vq_parallel")
+
     def set_pixelcnn_mode(self, mode):
         self._check(self.L.ts_set_pixelcnn_mode(self.h, mode), "ts_set_pixelcnn_mode")
 

@@ -201,6 +201,13 @@ def test_body_generate_fused_b12(eng, ckpts):
     assert (poses.cpu() - ref_poses).abs().max().item() <= TOL
     # diversity: different noise rows give different sequences
     assert len({tuple(c.flatten().tolist()) for c in codes.cpu()}) > 1
+    # the two VQ decoders side by side on two streams (default for batches <= 16) or one after the other: bit-identical
+    try:
+        eng.set_vq_parallel(0)
+        codes_seq, poses_seq = eng.body_generate(mfcc, label, noise)
+    finally:
+        eng.set_vq_parallel(16)
+    assert torch.equal(codes_seq, codes) and torch.equal(poses_seq, poses)
 
 
 def test_pixelcnn_6d_geometry():
