@@ -305,12 +305,19 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
   const ts_tensor* cls0 = ck.get("layers.0.class_cond_embedding.weight");
   const int ncls = (int)cls0->shape[0];
 
-  PixelPlan* P = new PixelPlan();
+  std::unique_ptr<PixelPlan> owner(new PixelPlan());   // released to the caller at the end; a failed build frees it
+  PixelPlan* P = owner.get();
   P->L = L;
   P->ncta = e->sm_count;
   // ts_set_pixelcnn_ctas: a plan for FEWER persistent CTAs than SMs leaves whole TPCs free for kernels of another
   // stream (the face regressor runs beside the latency-bound sampler when the per-GPU batch is small)
-  if (e->pixel_ctas >= PIX_MB && e->pixel_ctas <= e->sm_count) P->ncta = e->pixel_ctas & ~1;
+  if (e->pixel_ctas > 0) {
+    if (e->pixel_ctas < PIX_MB || e->pixel_ctas > e->sm_count) {
+      const int n = e->pixel_ctas, sms = e->sm_count;
+      fail(TS_ERR_UNSUPPORTED, "pixelcnn plan: ts_set_pixelcnn_ctas(%d) outside [%d, %d] (one CTA per sample of a 64-sample tile; SM count)", n, PIX_MB, sms);
+    }
+    P->ncta = e->pixel_ctas & ~1;
+  }
   if (const char* v = getenv("TS_PIX_CTAS")) {   // experiment switch: persistent CTAs (every CTA re-reads the stage's activations from L2)
     const int n = atoi(v);
     if (n >= PIX_MB && n <= e->sm_count) P->ncta = n;
@@ -437,7 +444,7 @@ static PixelPlan* build_plan(ts_engine* e, const Ckpt& ck, int level) {
     P->d_arena = (float*)e->dmalloc((size_t)P->lay.total * sizeof(float) + 256);
     P->d_barrier = (unsigned*)e->dmalloc(4096);   // one flag word per CTA
   }
-  return P;
+  return owner.release();
 }
 
 // =============================================================================================

@@ -106,3 +106,52 @@ def test_plan_sampling_with_prefix(plan, ckpts):
     got, _ = PE.run(p, sd["embedding.weight"].numpy(), cls_w, av, ah, label.numpy(), pre.numpy(), T0 + T,
                     noise=noise.numpy(), T0=T0)
     assert np.array_equal(got[:, T0:], ref.numpy())
+
+
+WBUF, MAXROWS = 18560, 16        # csrc/pixelcnn.h: floats per weight staging buffer, accumulator rows per CTA
+
+
+@pytest.mark.parametrize("level,ctas", [(1, 96), (1, 98), (1, 110), (1, 126), (1, 128), (1, 146), (2, 80), (2, 82), (2, 86),
+                                        (2, 94), (2, 112), (2, 128), (2, 130), (2, 148)])
+def test_plan_invariants_over_cta_counts(ckpts, level, ctas):
+    """ts_set_pixelcnn_ctas: every even count the stage table allows gives a plan the kernel can run — each task's weight slab
+    fits one staging buffer, at most 16 rows per CTA, every output row of every job owned exactly once, the same set of
+    (job, layer, column) per row whatever the count."""
+    e = Engine(-148)
+    e.set_pixelcnn_fusion(level)
+    e.set_pixelcnn_ctas(ctas)
+    e.load_pixelcnn(ckpts["pixel"]["generator"])
+    table, blob = _lib.plan_to_numpy(e.h)
+    e.close()
+    p = PE.Plan(table, blob)
+    assert p.ncta == ctas
+    t = p.table
+    mm = t[:, :, 6] > 0
+    assert ((t[:, :, 6] + 1) * t[:, :, 7])[mm].max() <= WBUF            # (K + 1) x padded rows
+    assert t[:, :, 4][mm].max() <= MAXROWS and (t[:, :, 7] % 4 == 0).all()
+    assert (t[:, :, 5][mm] + ((t[:, :, 6] + 1) * t[:, :, 7])[mm]).max() <= len(blob)
+    jobs = {}
+    for s in range(p.nstages):
+        for epi, layer, col, r0, n in t[s][:, :5].tolist():
+            if epi not in (0, 10):
+                jobs.setdefault((epi, layer, col), []).append((r0, n))
+    want = {1: 512, 2: 512, 3: 512, 4: 256, 5: 512, 6: 256, 11: 256, 12: 512, 13: 512, 9: 2048, 14: 512}   # output rows per job kind
+    for (epi, layer, col), rows in jobs.items():
+        rows.sort()
+        pos = 0
+        for r0, n in rows:
+            assert r0 == pos and n > 0, (epi, layer, col, rows)
+            pos += n
+        assert pos == want[epi], (epi, layer, col, pos)
+    n_v2h = sum(1 for k in jobs if k[0] in (3, 14))
+    assert n_v2h == (15 if level == 1 else 1 + 2 * 14)                 # per layer (both columns in two passes) / per layer and column
+
+
+@pytest.mark.parametrize("level,ctas", [(1, 94), (1, 64), (2, 78), (0, 96), (1, 32), (1, 150)])
+def test_plan_rejects_too_few_ctas(ckpts, level, ctas):
+    e = Engine(-148)
+    e.set_pixelcnn_fusion(level)
+    e.set_pixelcnn_ctas(ctas)
+    with pytest.raises(RuntimeError, match="pixelcnn plan"):
+        e.load_pixelcnn(ckpts["pixel"]["generator"])
+    e.close()
