@@ -61,12 +61,19 @@ class TrainWrapper:
     def load_state_dict(self, state_dict):
         """ckpt['generator'] of a body-pixel checkpoint (nets/smplx_body_pixel.py:115-142)."""
         sd = {k: (strip_module(v) if v is not None else None) for k, v in state_dict.items() if isinstance(v, dict) or v is None}
-        if "generator" in sd:
-            self.engine.load_pixelcnn(sd["generator"])
-        else:
-            self.engine.load_pixelcnn(strip_module(state_dict))
+        gen = sd["generator"] if "generator" in sd else strip_module(state_dict)
+        self.engine.load_pixelcnn(gen)
+        self._loaded = {"generator": gen, "audioencoder": None}
         if sd.get("audioencoder") is not None:
             self.engine.load_audioenc(sd["audioencoder"])
+            self._loaded["audioencoder"] = sd["audioencoder"]
+
+    def state_dict(self):
+        """The nested layout the reference saves (nets/smplx_body_pixel.py:104-113): the weights that were loaded (the engine
+        keeps repacked copies only), optimizer / discriminator slots empty — this is an inference engine."""
+        loaded = getattr(self, "_loaded", {"generator": None, "audioencoder": None})
+        return {"generator": loaded["generator"], "generator_optim": None, "audioencoder": loaded["audioencoder"],
+                "audioencoder_optim": None, "discriminator": None, "discriminator_optim": None}
 
     # -- inference -------------------------------------------------------------------------------
     def _noise(self, T, B):
@@ -102,20 +109,36 @@ class TrainWrapper:
         self.last_codes = codes
         return poses
 
+    def infer(self, aud_feat, frame, id, B, pre_latents=None, pre_audio=None, pre_pose=None):
+        """The reference's inner call (:291-304): aud_feat [B,M,64] (time-major features of ONE chunk) ->
+        (latents [B,T,2], audio [B,256,T,2], body [B,39,4T], hand [B,90,4T]).  ``pre_latents`` / ``pre_audio`` (the first
+        two results of the previous chunk's call) condition the sampler on that chunk (GatedPixelCNN.generate :158-165);
+        ``pre_pose`` is accepted and unused like in the reference, whose Decoder.forward ignores ``pre_state``
+        (nets/spg/vqvae_1d.py:139-149) — each chunk is decoded on its own."""
+        a = self.engine.audio_encode(aud_feat.transpose(1, 2).contiguous())            # [B,256,T]
+        T = a.shape[2]
+        label = id.reshape(-1)
+        if pre_latents is None:
+            latents = self.engine.pixelcnn_generate(a, label, self._noise(T, B))
+        else:
+            pa = pre_audio[..., 0] if pre_audio.dim() == 4 else pre_audio              # [B,256,T0]
+            latents = self.engine.pixelcnn_generate(torch.cat([pa.to(a.device), a], 2), label, self._noise(T, B), T=T,
+                                                    pre_latents=pre_latents)
+        body = self.engine.vq_decode(0, latents[..., 0].contiguous())
+        hand = self.engine.vq_decode(1, latents[..., 1].contiguous())
+        return latents, a.unsqueeze(-1).repeat(1, 1, 1, 2), body, hand
+
     def _infer_continuity(self, aud_fn, id, fps, sr, B):
-        """continuity=True (:244-269, infer :291-304): a 2 s prefix, then the rest conditioned on the prefix's latents
-        and audio (GatedPixelCNN.generate(pre_latents, pre_audio)).  The two chunks go through the audio encoder
-        separately and are DECODED separately — the reference's Decoder.forward ignores pre_state
-        (nets/spg/vqvae_1d.py:139-149), so each chunk sees zero padding at the 2 s seam."""
+        """continuity=True (:244-269): a 2 s prefix, then the rest conditioned on the prefix's latents and audio.  The two
+        chunks go through the audio encoder separately and are DECODED separately, so each chunk sees zero padding at the
+        2 s seam."""
         aud_feat, gap = get_mfcc_sepa(aud_fn, sr=sr, fps=fps)                 # (M0+M1, 64), M0
-        feat = torch.from_numpy(np.ascontiguousarray(np.asarray(aud_feat, dtype=np.float32).T))[None].repeat(B, 1, 1)
-        m0, m1 = feat[:, :, :gap].contiguous(), feat[:, :, gap:].contiguous()
+        feat = torch.from_numpy(np.ascontiguousarray(np.asarray(aud_feat, dtype=np.float32)))[None].repeat(B, 1, 1)   # [B,M,64]
         label = torch.tensor([0]) if id is None else id.reshape(-1).repeat(B)
-        a0, a1 = self.engine.audio_encode(m0), self.engine.audio_encode(m1)
-        T0, T1 = a0.shape[2], a1.shape[2]
-        lat0 = self.engine.pixelcnn_generate(a0, label, self._noise(T0, B))
-        lat1 = self.engine.pixelcnn_generate(torch.cat([a0, a1], 2), label, self._noise(T1, B), T=T1, pre_latents=lat0)
+        pre_pose = {"b": None, "h": None}
+        lat0, audio0, body_0, hand_0 = self.infer(feat[:, :gap], 0, label, B, pre_pose=pre_pose)
+        pre_pose["b"], pre_pose["h"] = body_0[:, :, -4:].transpose(1, 2), hand_0[:, :, -4:].transpose(1, 2)
+        lat1, _, body_1, hand_1 = self.infer(feat[:, gap:], 0, label, B, lat0, audio0, pre_pose)
         self.last_codes = torch.cat([lat0, lat1], 1)
-        body = torch.cat([self.engine.vq_decode(0, lat[..., 0].contiguous()) for lat in (lat0, lat1)], 2)
-        hand = torch.cat([self.engine.vq_decode(1, lat[..., 1].contiguous()) for lat in (lat0, lat1)], 2)
+        body, hand = torch.cat([body_0, body_1], 2), torch.cat([hand_0, hand_1], 2)
         return torch.cat([body, hand], 1).transpose(1, 2).cpu().numpy()

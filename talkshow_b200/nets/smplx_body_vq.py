@@ -26,8 +26,16 @@ class TrainWrapper:
 
     def load_state_dict(self, state_dict):
         """{'g_body': sd, 'g_hand': sd} (nets/smplx_body_vq.py:297-302)."""
-        self.engine.load_vq(0, strip_module(state_dict["g_body"]))
-        self.engine.load_vq(1, strip_module(state_dict["g_hand"]))
+        self._loaded = {"g_body": strip_module(state_dict["g_body"]), "g_hand": strip_module(state_dict["g_hand"])}
+        self.engine.load_vq(0, self._loaded["g_body"])
+        self.engine.load_vq(1, self._loaded["g_hand"])
+
+    def state_dict(self):
+        """nets/smplx_body_vq.py:77-94 (composition): the loaded weights in the layout the reference saves; optimizer and
+        discriminator slots empty."""
+        loaded = getattr(self, "_loaded", {"g_body": None, "g_hand": None})
+        return {"g_body": loaded["g_body"], "g_body_optim": None, "g_hand": loaded["g_hand"], "g_hand_optim": None,
+                "discriminator": None, "discriminator_optim": None}
 
     def encode(self, initial_pose):
         """initial_pose (B,165,F) -> (idx_body [B,T], idx_hand [B,T]) int64 on the device."""

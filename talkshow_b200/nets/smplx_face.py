@@ -26,7 +26,13 @@ class TrainWrapper:
     def load_state_dict(self, state_dict):
         """ckpt['generator'] of a face checkpoint: {'generator': Generator sd, ...} (nets/base.py:38-54)."""
         sd = state_dict["generator"] if "generator" in state_dict else state_dict
-        self.engine.load_face(strip_module(sd))
+        self._loaded = strip_module(sd)
+        self.engine.load_face(self._loaded)
+
+    def state_dict(self):
+        """nets/base.py:29-36: {'generator': ..., optimizer / discriminator slots empty}."""
+        return {"generator": getattr(self, "_loaded", None), "generator_optim": None, "discriminator": None,
+                "discriminator_optim": None}
 
     def infer_on_audio(self, aud_fn, id=None, initial_pose=None, norm_stats=None, w_pre=False, frame=None, am=None,
                        am_sr=16000, **kwargs):
