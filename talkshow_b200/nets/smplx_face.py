@@ -9,7 +9,35 @@ from ..data_utils.utils import get_mfcc_ta
 from .base import resolve_device, shared_engine, strip_module
 
 
+_HF_TORCH_LAYERDROP = None
+
+
+def hf_layerdrop_uses_torch_rng():
+    """Does the installed ``transformers`` draw the wav2vec2 encoder's LayerDrop probabilities from TORCH's default CPU
+    generator?  Newer releases do — ``dropout_probability = torch.rand([])`` once per encoder layer per forward, in eval
+    mode too — so the reference's face pass (nets/spg/wav2vec.py:76-143 -> Wav2Vec2Encoder.forward) moves the generator
+    that the PixelCNN sampler of the following body pass draws from (scripts/demo.py:173-204).  The release the reference
+    pins (transformers~=4.22.1, requirements.txt:2) used ``np.random.uniform`` there and left torch's generator alone."""
+    global _HF_TORCH_LAYERDROP
+    if _HF_TORCH_LAYERDROP is None:
+        try:
+            import inspect
+
+            from transformers.models.wav2vec2 import modeling_wav2vec2 as m
+
+            _HF_TORCH_LAYERDROP = "torch.rand(" in inspect.getsource(m.Wav2Vec2Encoder.forward)
+        except Exception:
+            _HF_TORCH_LAYERDROP = False
+    return _HF_TORCH_LAYERDROP
+
+
 class TrainWrapper:
+    # torch.rand([]) draws consumed from the default CPU generator per forward, so that a seeded run of the demo flow samples
+    # the same body codes as the reference does in the same environment.  None: what the reference would consume with the
+    # installed transformers (one per encoder layer if hf_layerdrop_uses_torch_rng(), else 0); an int forces it (0 = the
+    # behaviour of the pinned transformers 4.22.1).  The regressor itself is deterministic either way.
+    layerdrop_rng_draws = None
+
     def __init__(self, args, config, engine=None):
         self.args = args
         self.config = config
@@ -28,6 +56,7 @@ class TrainWrapper:
         sd = state_dict["generator"] if "generator" in state_dict else state_dict
         self._loaded = strip_module(sd)
         self.engine.load_face(self._loaded)
+        self.encoder_layers = len({k.split(".")[3] for k in self._loaded if k.startswith("audio_encoder.encoder.layers.")})
 
     def state_dict(self):
         """nets/base.py:29-36: {'generator': ..., optimizer / discriminator slots empty}."""
@@ -54,10 +83,18 @@ class TrainWrapper:
             idv = F.one_hot(id.reshape(-1).to(torch.int64), self.num_classes).to(torch.float32)
         return self.generate_ids(wave, idv, frame).cpu().numpy()
 
+    def _mirror_reference_rng(self):
+        n = self.layerdrop_rng_draws
+        if n is None:
+            n = getattr(self, "encoder_layers", 0) if hf_layerdrop_uses_torch_rng() else 0
+        for _ in range(int(n)):
+            torch.rand([])
+
     def generate_ids(self, wave, idv, frame):
+        self._mirror_reference_rng()
         return self.engine.face_forward(wave, idv, frame)
 
     def generate(self, wv2_feat, frame):
         """tensor API (:221-238): wv2_feat [B,1,N] -> torch (B, frame, 103); id = zeros."""
         wave = wv2_feat.to(torch.float32).reshape(wv2_feat.shape[0], -1)
-        return self.engine.face_forward(wave, torch.zeros(wave.shape[0], self.num_classes), frame)
+        return self.generate_ids(wave, torch.zeros(wave.shape[0], self.num_classes), frame)

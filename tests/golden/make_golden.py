@@ -48,6 +48,7 @@ def main():
     args = ap.parse_args()
     cwd = os.getcwd()
     nets = import_reference()
+    REF_DIR = os.getcwd()
     import nets.smplx_body_pixel as ref_bp
     import nets.smplx_body_vq as ref_vq
     import nets.smplx_face as ref_face
@@ -223,6 +224,71 @@ def main():
         out = matrix_to_axis_angle(rotation_6d_to_matrix(d6))
         np.savez_compressed(os.path.join(HERE, "rot6d.npz"), d6=d6.numpy(), aa=out.numpy())
         print("rot6d", d6.shape, float(out.abs().max()), bool(torch.isfinite(out).all()))
+    # ---- the whole demo flow: scripts/demo.py:158-246 (infer) of the reference, file in -> .npy out ---------------------
+    if want("demo_flow"):
+        import importlib.machinery
+        from scipy.io import wavfile
+
+        class _RenderTool:                              # visualise/rendering.py needs pyrender / ffmpeg: out of scope
+            def __init__(self, *aa, **kk):
+                self.calls = []
+
+            def _render_sequences(self, wav, vertices_list, **kk):
+                self.calls.append((wav, len(vertices_list), kk))
+
+        for name, attrs in (("visualise", {}), ("visualise.rendering", {"RenderTool": _RenderTool})):
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            m.__path__ = []
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+        import data_utils.utils as ref_du
+        import scripts.demo as ref_demo
+        import transformers
+        from talkshow_b200.nets.smplx_face import hf_layerdrop_uses_torch_rng   # reads transformers' source only
+        from talkshow_b200.data_utils.utils import load_wav
+
+        # file decoding: torchaudio.load needs torchcodec and librosa is a stub here; both readers return the
+        # samples of the 16 kHz int16 file unchanged, which is what the real ones do for such a file
+        ref_du.ta.load = lambda fn: load_wav(fn)
+        ref_du.librosa.load = lambda fn, sr=16000: (load_wav(fn)[0].mean(0).numpy(), 16000)
+        ref_demo.Wav2Vec2Processor.from_pretrained = staticmethod(lambda name: object())      # hub download; only `am is None` is tested
+        # the module-level stubs above replaced the patched readers of the earlier sections: restore the real feature code
+        ref_bp.get_mfcc_ta = ref_du.get_mfcc_ta
+        sec, nsamp, spk, seed = 3, 3, 2, 321
+        x = (synth.synth_wave(1, 16000 * sec, seed=41)[0].numpy() * 20000).astype(np.int16)
+        wav = os.path.join(tmp, "clip one.wav")
+        wavfile.write(wav, 16000, x)
+        torch.save({"generator": bp_ckpt}, os.path.join(tmp, "body.pth"))
+        torch.save({"generator": face_ckpt}, os.path.join(tmp, "face.pth"))
+        from trainer.options import parse_args as ref_parse_args
+        dargs = ref_parse_args().parse_args(["--config_file", "config/body_pixel.json", "--infer", "--audio_file", wav, "--id", str(spk),
+                                             "--num_sample", str(nsamp), "--body_model_path", os.path.join(tmp, "body.pth"),
+                                             "--face_model_path", os.path.join(tmp, "face.pth")])
+        dargs.gpu = "cpu"
+        g_body = ref_demo.init_model(dargs.body_model_name, dargs.body_model_path, dargs, cfg_pixel)
+        g_face = ref_demo.init_model(dargs.face_model_name, dargs.face_model_path, dargs, cfg_face)
+
+        class _Smplx:                                   # smplx is not installed: get_vertices only needs .vertices / .body_pose
+            def __call__(self, **kw):
+                return types.SimpleNamespace(vertices=torch.zeros(1, 4, 3), body_pose=kw["body_pose"])
+
+        rt = _RenderTool()
+        os.makedirs(os.path.join(tmp, "visualise", "video", cfg_pixel.Log.name), exist_ok=True)
+        os.chdir(tmp)                                   # infer() saves relative to the working directory
+        torch.manual_seed(seed)
+        ref_demo.infer(g_body, g_face, _Smplx(), rt, cfg_pixel, dargs)
+        saved = np.load(os.path.join(tmp, "visualise", "video", cfg_pixel.Log.name, "clip one.npy"))
+        frame = 16000 * sec * 30 // 16000
+        assert saved.shape == (nsamp * frame, 265) and len(rt.calls) == 1 and rt.calls[0][1] == nsamp
+        torch.manual_seed(seed)
+        n_first = draw_noise(2 * 22, 1)                 # sample 0's draws: M = 90 feature frames -> T = 22 latent rows
+        np.savez_compressed(os.path.join(HERE, "demo_flow.npz"), saved=saved[::2].copy(), saved_stride=2, seconds=sec, num_sample=nsamp,
+                            speaker=spk, seed=seed, wave_seed=41, log_name=str(cfg_pixel.Log.name), frame=frame, noise_fp=noise_fp(n_first),
+                            hf_torch_layerdrop=int(hf_layerdrop_uses_torch_rng()), transformers_version=transformers.__version__)
+        os.chdir(REF_DIR)
+        print("demo_flow", saved.shape, float(np.abs(saved).max()))
     # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
     if want("options"):
         import json

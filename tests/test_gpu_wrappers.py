@@ -29,6 +29,18 @@ def _load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
+def _reference_face_pass_rng(g_face):
+    """What the reference's face pass does to torch's default generator before the body samples are drawn
+    (scripts/demo.py:173-204): with the installed transformers the wav2vec2 encoder draws one torch.rand([]) per layer
+    (LayerDrop probability, eval mode included); the release the reference pins drew from numpy's generator instead."""
+    from talkshow_b200.nets.smplx_face import hf_layerdrop_uses_torch_rng
+
+    assert g_face.layerdrop_rng_draws is None and g_face.encoder_layers == 12
+    if hf_layerdrop_uses_torch_rng():
+        for _ in range(12):
+            torch.rand([])
+
+
 def test_body_pixel_wrapper_infer_on_audio(ckpts, tmp_path):
     """BASELINE config 3 through the wrapper: vq checkpoint picked up from config.Model.vq_path like the
     reference ctor (smplx_body_pixel.py:59-62), features passed as an array, CPU-generator noise."""
@@ -242,6 +254,7 @@ def test_demo_flow_matches_reference_flow(ckpts, tmp_path, monkeypatch):
     mfcc = torch.from_numpy(mfcc_from_wave(audio, sr, sr=22000, fps=30).T.copy())[None]
     T = O.latent_rows(mfcc.shape[2])
     torch.manual_seed(seed)
+    _reference_face_pass_rng(g_face)
     for i in range(nsamp):
         noise = torch.stack([torch.empty(1, 2048).exponential_(1) for _ in range(2 * T)])
         _, body = O.body_generate(ckpts["pixel"], ckpts["vq"], mfcc, torch.tensor([spk]), noise=noise, window=18)
@@ -252,3 +265,10 @@ def test_demo_flow_matches_reference_flow(ckpts, tmp_path, monkeypatch):
     assert saved.shape == (nsamp * frame, 265)                       # scripts/demo.py:239-245
     assert np.array_equal(saved, np.concatenate([r.cpu().numpy() for r in result_list], 0))
     assert not np.array_equal(saved[:frame], saved[frame:2 * frame])      # diversity samples differ
+    # the file the REFERENCE's own scripts/demo.py:infer writes for the same wav, checkpoints, command line and seed
+    # (tests/golden/make_golden.py --only demo_flow), when this host's CPU generator gives the stream it was made with
+    gold = _load("demo_flow")
+    assert (sec, nsamp, spk, seed) == (int(gold["seconds"]), int(gold["num_sample"]), int(gold["speaker"]), int(gold["seed"]))
+    from talkshow_b200.nets.smplx_face import hf_layerdrop_uses_torch_rng
+    if np.allclose(gold["noise_fp"], noise_fp(draw_noise(2 * T, 1, seed)), rtol=0, atol=1e-9) and hf_layerdrop_uses_torch_rng() == bool(gold["hf_torch_layerdrop"]):
+        assert np.abs(saved[::int(gold["saved_stride"])] - gold["saved"]).max() <= 1e-4
