@@ -282,10 +282,21 @@ def main():
         saved = np.load(os.path.join(tmp, "visualise", "video", cfg_pixel.Log.name, "clip one.npy"))
         frame = 16000 * sec * 30 // 16000
         assert saved.shape == (nsamp * frame, 265) and len(rt.calls) == 1 and rt.calls[0][1] == nsamp
+        # the --stand and --only_face branches (scripts/demo.py:165-169,224-227; part2full(pred, stand))
+        variants = {}
+        for key, flags in (("stand", ["--stand"]), ("only_face", ["--only_face"])):
+            vargs = ref_parse_args().parse_args(["--config_file", "config/body_pixel.json", "--infer", "--audio_file", wav, "--id", str(spk),
+                                                 "--num_sample", "1", "--body_model_path", os.path.join(tmp, "body.pth"),
+                                                 "--face_model_path", os.path.join(tmp, "face.pth")] + flags)
+            torch.manual_seed(seed)
+            ref_demo.infer(g_body, g_face, _Smplx(), rt, cfg_pixel, vargs)
+            variants[key] = np.load(os.path.join(tmp, "visualise", "video", cfg_pixel.Log.name, "clip one.npy"))
+            assert variants[key].shape == (frame, 265)
         torch.manual_seed(seed)
         n_first = draw_noise(2 * 22, 1)                 # sample 0's draws: M = 90 feature frames -> T = 22 latent rows
         np.savez_compressed(os.path.join(HERE, "demo_flow.npz"), saved=saved[::2].copy(), saved_stride=2, seconds=sec, num_sample=nsamp,
                             speaker=spk, seed=seed, wave_seed=41, log_name=str(cfg_pixel.Log.name), frame=frame, noise_fp=noise_fp(n_first),
+                            saved_stand=variants["stand"][::3].copy(), saved_only_face=variants["only_face"][::3].copy(),
                             hf_torch_layerdrop=int(hf_layerdrop_uses_torch_rng()), transformers_version=transformers.__version__)
         os.chdir(REF_DIR)
         print("demo_flow", saved.shape, float(np.abs(saved).max()))

@@ -213,6 +213,14 @@ def test_demo_flow_on_the_oracle_engine(ckpts, tmp_path, monkeypatch, shared):
     from talkshow_b200.nets.smplx_face import hf_layerdrop_uses_torch_rng
     if hf_layerdrop_uses_torch_rng() == bool(gold["hf_torch_layerdrop"]):       # same transformers behaviour as when the fixture was made
         assert np.abs(saved[::int(gold["saved_stride"])] - gold["saved"]).max() <= 1e-5      # == the file the reference's demo.py writes
+        # --stand / --only_face (scripts/demo.py:165-169,224-227), one sample each, same seed
+        for key, flag in (("saved_stand", "--stand"), ("saved_only_face", "--only_face")):
+            vargs = parse_args().parse_args(["--config_file", os.path.join(ROOT, "config", "body_pixel.json"), "--infer", "--audio_file", wav,
+                                             "--id", str(spk), "--num_sample", "1", "--body_model_path", str(tmp_path / "body.pth"),
+                                             "--face_model_path", str(tmp_path / "face.pth"), flag])
+            torch.manual_seed(seed)
+            res, _ = demo.infer(g_body, g_face, None, None, config, vargs, save=False)
+            assert np.abs(res[0].numpy()[::3] - gold[key]).max() <= 1e-5, key
     # the pinned transformers (no torch draws in the face pass): forced by the attribute, differs from the auto mode exactly then
     g_face.layerdrop_rng_draws = 0
     torch.manual_seed(seed)
