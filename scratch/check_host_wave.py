@@ -1,4 +1,6 @@
-"""generate() with the waveform as a pinned host tensor (copy enqueued behind the body path) == device inputs; e2e time of both orders."""
+"""Host-buffer step with every input copied before generate() vs the public generate_host(); body-path breakdown at 8 / 1 clips.
+(profiles/r02c_host_copy_order_and_body_breakdown.log was taken with a pipeline variant that enqueued the waveform copy behind the body
+path's launch inside generate(): no measurable gain, not kept — with the committed pipeline both orders are the same code path.)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
