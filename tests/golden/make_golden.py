@@ -209,6 +209,17 @@ def main():
                             wave_head=wave[0, :64].numpy(),
                             fp=np.array(list(synth.fingerprint(face_ckpt).values())))
         print("face", o1.shape, float(np.abs(o1).max()), o2.shape)
+    # ---- face at the benchmarked clip length: 10 s, two clips with speaker ids (config 5's face half, per clip) ---------------
+    if want("face_10s"):
+        gf = ref_face.TrainWrapper(a, cfg_face)
+        gf.load_state_dict(face_ckpt)
+        gf.generator.eval()
+        wave = synth.synth_wave(2, 160000, seed=8)
+        ids = torch.tensor([2, 0])
+        o = gf.generator(wave[:, None, :], None, torch.nn.functional.one_hot(ids, 4), time_steps=300)[0].numpy()     # (2,300,103)
+        np.savez_compressed(os.path.join(HERE, "face_10s.npz"), out=o[:, ::4].copy(), out_stride=4, out_head=o[:, :8].copy(), ids=ids.numpy(),
+                            wave_seed=8, fp=np.array(list(synth.fingerprint(face_ckpt).values())))
+        print("face_10s", o.shape, float(np.abs(o).max()))
     # ---- 6-D rotation -> axis-angle (demo.py:185-188,216-219 for convert_to_6d configs) ----------
     if want("rot6d"):
         from data_utils.rotation_conversion import matrix_to_axis_angle, rotation_6d_to_matrix, axis_angle_to_matrix, matrix_to_rotation_6d

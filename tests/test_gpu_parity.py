@@ -303,6 +303,12 @@ def test_face_vs_oracle_10s(face_eng, ckpts):
     err = (got - ref).abs().max().item()
     print("face 10 s max-abs err vs oracle: %.3e" % err)
     assert err <= TOL
+    # the same two clips from the reference itself (tests/golden/make_golden.py --only face_10s)
+    g = _load("face_10s")
+    assert int(g["wave_seed"]) == 8 and g["ids"].tolist() == [2, 0]
+    gerr = max(np.abs(got.numpy()[:, ::int(g["out_stride"])] - g["out"]).max(), np.abs(got.numpy()[:, :8] - g["out_head"]).max())
+    print("face 10 s max-abs err vs reference golden: %.3e" % gerr)
+    assert gerr <= TOL
 
 
 def test_device_mfcc_matches_torchaudio(eng):

@@ -142,6 +142,17 @@ def test_face(ckpts):
     assert np.abs(out2.numpy() - g["out_b2"]).max() <= 2e-5
 
 
+def test_face_10s(ckpts):
+    """the benchmarked clip length (10 s -> 300 frames), two clips with speaker ids, reference-generated golden."""
+    g = _load("face_10s")
+    wave = synth.synth_wave(2, 160000, seed=int(g["wave_seed"]))
+    ids = torch.nn.functional.one_hot(torch.tensor(g["ids"]), 4).float()
+    out = O.face_forward(ckpts["face"]["generator"], wave, ids, 300).numpy()
+    assert out.shape == (2, 300, 103)
+    err = max(np.abs(out[:, ::int(g["out_stride"])] - g["out"]).max(), np.abs(out[:, :8] - g["out_head"]).max())
+    assert err <= 2e-5, err
+
+
 def test_pose_assembly_layout():
     face = torch.arange(5 * 103, dtype=torch.float32).view(5, 103)
     body = torch.arange(4 * 129, dtype=torch.float32).view(4, 129) + 1000
