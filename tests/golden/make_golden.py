@@ -311,6 +311,23 @@ def main():
                             hf_torch_layerdrop=int(hf_layerdrop_uses_torch_rng()), transformers_version=transformers.__version__)
         os.chdir(REF_DIR)
         print("demo_flow", saved.shape, float(np.abs(saved).max()))
+    # ---- the outputs the reference SHIPS (demo/**/*.npy, written by scripts/demo.py:239-245 with the authors' checkpoints): layout,
+    #      the constant lower-body columns part2full inserts (data_utils/lower_body.py:68-87), the --only_face static block ----
+    if want("demo_npy_layout"):
+        import glob
+        import json
+        lower = [i for i in range(265) if not (i < 3 or 18 <= i < 21 or 27 <= i < 30 or 36 <= i < 39 or i >= 45)]      # 33 inserted columns
+        files = {}
+        for f in sorted(glob.glob("demo/**/*.npy", recursive=True)):
+            arr = np.load(f)
+            assert arr.ndim == 2 and arr.shape[1] == 265 and arr.dtype == np.float32
+            lc = arr[:, lower]
+            assert (lc == lc[0]).all()                                                   # constant over the frames of a file
+            static = arr[:, 3:165]
+            files[f] = {"rows": int(arr.shape[0]), "lower": [float(v) for v in lc[0]],
+                        "only_face_static": [float(v) for v in static[0]] if (static == static[0]).all() else None}
+        json.dump({"lower_columns": lower, "files": files}, open(os.path.join(HERE, "demo_npy_layout.json"), "w"), indent=1, sort_keys=True)
+        print("demo_npy_layout", len(files))
     # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
     if want("options"):
         import json

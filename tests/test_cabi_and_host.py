@@ -114,6 +114,35 @@ def test_pose_layout_helpers():
     assert part2full(x).shape == (3, 265)
 
 
+def test_pose_layout_matches_the_files_the_reference_ships():
+    """demo/**/*.npy of the reference (written by its scripts/demo.py with the authors' checkpoints): (num_sample*F, 265) float32,
+    the 33 columns part2full inserts are constant per file and equal this package's table in the sitting or the --stand variant; the
+    --only_face file has the static 162-value body block.  Fixture: tests/golden/make_golden.py --only demo_npy_layout."""
+    import json
+
+    from talkshow_b200.data_utils.lower_body import part2full
+
+    g = json.load(open(os.path.join(GOLDEN, "demo_npy_layout.json")))
+    cols = g["lower_columns"]
+    assert len(cols) == 33 and len(g["files"]) >= 8
+    zero = torch.zeros(1, 232)
+    sit = part2full(zero)[0, cols].tolist()
+    stand = part2full(zero, stand=True)[0, cols].tolist()
+    assert part2full(zero).shape == (1, 265) and sit != stand
+    kinds = set()
+    for name, f in g["files"].items():
+        low = [np.float32(v) for v in f["lower"]]
+        kind = "sit" if low == [np.float32(v) for v in sit] else "stand" if low == [np.float32(v) for v in stand] else None
+        assert kind is not None, name
+        kinds.add(kind)
+        if f["only_face_static"] is not None:                       # scripts/demo.py:165-169,226-227
+            static = torch.zeros(162)
+            static[6:9] = torch.tensor([3.0747, -0.0158, -0.0152])
+            assert [np.float32(v) for v in f["only_face_static"]] == [np.float32(v) for v in static.tolist()], name
+            kinds.add("only_face")
+    assert kinds == {"sit", "stand", "only_face"}
+
+
 def test_shard_ranges_cover_batch():
     from talkshow_b200.pipeline import shard_range
 
