@@ -328,6 +328,24 @@ def main():
                         "only_face_static": [float(v) for v in static[0]] if (static == static[0]).all() else None}
         json.dump({"lower_columns": lower, "files": files}, open(os.path.join(HERE, "demo_npy_layout.json"), "w"), indent=1, sort_keys=True)
         print("demo_npy_layout", len(files))
+    # ---- host audio front-end: data_utils/utils.py:148-231 (get_mfcc_ta) and :234-263 (get_mfcc_sepa) on a stereo 44.1 kHz file ----
+    if want("frontend"):
+        from scipy.io import wavfile
+        import data_utils.utils as ref_du
+        from talkshow_b200.data_utils.utils import load_wav
+
+        ref_du.ta.load = lambda fn: load_wav(fn)          # torchaudio.load needs torchcodec here; same samples
+        x = (synth.synth_wave(2, 44100 * 5, seed=3).numpy().T * 20000).astype(np.int16)
+        wav = os.path.join(tmp, "stereo44k.wav")
+        wavfile.write(wav, 44100, x)
+        fe = {}
+        for fps in (30, 15):
+            fe["ta_%d" % fps] = ref_du.get_mfcc_ta(wav, sr=22000, fps=fps, smlpx=True, type="mfcc", am=None)
+            fe["sepa_%d" % fps], fe["gap_%d" % fps] = ref_du.get_mfcc_sepa(wav, sr=22000, fps=fps)
+        np.savez_compressed(os.path.join(HERE, "frontend.npz"), wave_seed=3, seconds=5, sr=44100,
+                            **{k: (v[::5].copy() if isinstance(v, np.ndarray) else v) for k, v in fe.items()},
+                            shapes=np.array([fe["ta_30"].shape[0], fe["ta_15"].shape[0], fe["sepa_30"].shape[0], fe["sepa_15"].shape[0]]))
+        print("frontend", fe["ta_30"].shape, fe["gap_30"], fe["gap_15"])
     # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
     if want("options"):
         import json

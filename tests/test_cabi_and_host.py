@@ -168,6 +168,27 @@ def test_noise_contract_matches_reference_multinomial():
     assert torch.equal(torch.argmax(probs / q, -1), ref)
 
 
+def test_front_end_matches_reference_functions(tmp_path):
+    """get_mfcc_ta / get_mfcc_sepa (30 and 15 fps) on a stereo 44.1 kHz int16 file == the reference's functions on the same file
+    (fixture: tests/golden/make_golden.py --only frontend; same torchaudio transforms, so the features are identical)."""
+    from scipy.io import wavfile
+
+    from talkshow_b200.data_utils.utils import get_mfcc_sepa, get_mfcc_ta
+
+    g = np.load(os.path.join(GOLDEN, "frontend.npz"))
+    x = (synth.synth_wave(2, int(g["sr"]) * int(g["seconds"]), seed=int(g["wave_seed"])).numpy().T * 20000).astype(np.int16)
+    p = str(tmp_path / "stereo44k.wav")
+    wavfile.write(p, int(g["sr"]), x)
+    rows = []
+    for fps in (30, 15):
+        a = get_mfcc_ta(p, sr=22000, fps=fps, smlpx=True, type="mfcc", am=None)
+        b, gap = get_mfcc_sepa(p, sr=22000, fps=fps)
+        rows += [a.shape[0], b.shape[0]]
+        assert gap == int(g["gap_%d" % fps])
+        assert np.abs(a[::5] - g["ta_%d" % fps]).max() <= 1e-4 and np.abs(b[::5] - g["sepa_%d" % fps]).max() <= 1e-4
+    assert [rows[0], rows[2], rows[1], rows[3]] == g["shapes"].tolist()
+
+
 def test_mfcc_front_end_shapes(tmp_path):
     from scipy.io import wavfile
 
