@@ -74,7 +74,7 @@ def main():
     out = {}
 
     # ---- body pixel: wrapper end to end (config 3) ------------------------------------------
-    if want("pixel_b1_t30") or want("pixel_b3_t75") or want("pixel_cont") or want("wrapper_cont"):
+    if want("pixel_b1_t30") or want("pixel_b3_t75") or want("pixel_cont") or want("wrapper_cont") or want("wrapper_b3"):
         g = ref_bp.TrainWrapper(a, cfg_pixel)
         g.load_state_dict(bp_ckpt)            # demo.py:54-62 passes ckpt['generator'] = this dict
     if want("pixel_b1_t30"):
@@ -97,6 +97,18 @@ def main():
                             fp=np.array(list(synth.fingerprint(bp_ckpt).values())),
                             fp_vq=np.array(list(synth.fingerprint(vq_ckpt).values())))
         print("pixel_b1_t30", lat[0, :6].tolist(), pred.shape)
+
+    if want("wrapper_b3"):
+        # diversity through the wrapper's own batch argument (test_body.py:139-146 passes B): one clip, B = 3 samples, speaker 2,
+        # 15 fps default features injected as (M, 64)
+        mfcc = synth.synth_mfcc(1, 40, seed=515)
+        ref_bp.get_mfcc_ta = lambda *aa, **kk: mfcc[0].transpose(0, 1).numpy()
+        torch.manual_seed(SAMPLER_SEED + 5)
+        pred = g.infer_on_audio("synthetic.wav", id=torch.tensor([2]), B=3)        # (3, 40, 129)
+        torch.manual_seed(SAMPLER_SEED + 5)
+        noise = draw_noise(20, 3)
+        np.savez_compressed(os.path.join(HERE, "wrapper_b3.npz"), pred=pred, noise_fp=noise_fp(noise), sampler_seed=SAMPLER_SEED + 5, mfcc_seed=515)
+        print("wrapper_b3", pred.shape)
 
     if want("pixel_b3_t75"):
         mfcc = synth.synth_mfcc(3, 300, seed=77)

@@ -86,6 +86,14 @@ def test_body_pixel_wrapper_golden(ckpts, tmp_path, shared):
     assert np.array_equal(lat.numpy(), gold["codes"]) and audio.shape == (1, 256, 30, 2)
     assert body.shape == (1, 39, 120) and hand.shape == (1, 90, 120)
     assert np.abs(torch.cat([body, hand], 1).transpose(1, 2).numpy() - gold["pred"]).max() <= 1e-5
+    # diversity through the wrapper's batch argument: one clip, B = 3, speaker 2 (id [1] repeated like :253-256), reference golden
+    gb = _load("wrapper_b3")
+    feats = synth.synth_mfcc(1, 40, seed=int(gb["mfcc_seed"]))[0].t().numpy()
+    assert np.allclose(gb["noise_fp"], noise_fp(draw_noise(20, 3, int(gb["sampler_seed"]))), rtol=0, atol=1e-9)
+    torch.manual_seed(int(gb["sampler_seed"]))
+    pred3 = g.infer_on_audio(feats, id=torch.tensor([2]), B=3)
+    assert pred3.shape == (3, 40, 129) and np.abs(pred3 - gb["pred"]).max() <= 1e-5
+    assert not np.array_equal(pred3[0], pred3[1])
     with pytest.raises(NotImplementedError):
         init_model("s2g_LS3DCG", _args(), cfg)
     g.args.infer = False
