@@ -146,6 +146,7 @@ __global__ void assemble_kernel(const float* __restrict__ face, const float* __r
 extern "C" int ts_assemble_pose(ts_engine* e, const float* face, const float* body, float* out, int B, int Ff, int Fb,
                                 int stand, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (B <= 0 || Ff <= 0 || Fb <= 0) fail(TS_ERR_INVALID, "ts_assemble_pose: B=%d Ff=%d Fb=%d", B, Ff, Fb);
   long n = (long)B * Ff * 265;
   int blocks = (int)std::min<long>((n + 255) / 256, 148 * 8);
@@ -190,6 +191,7 @@ __global__ void rot6d_to_aa_kernel(const float* __restrict__ d6, float* __restri
 
 extern "C" int ts_rot6d_to_axis_angle(ts_engine* e, const float* d6, float* aa, int64_t n, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (n < 0) fail(TS_ERR_INVALID, "ts_rot6d_to_axis_angle: n=%lld", (long long)n);
   if (n > 0) {
     int blocks = (int)std::min<long>((n + 255) / 256, 148 * 8);
@@ -209,6 +211,7 @@ extern "C" int ts_vq_dim(ts_engine* e, int which) {
 extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* label, const float* noise,
                                 int64_t* codes, float* poses, int B, int M, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (!e->conv || !e->conv->audio_loaded) fail(TS_ERR_NOT_LOADED, "audio encoder weights not loaded");
   if (!e->conv->vq[0].loaded || !e->conv->vq[1].loaded) fail(TS_ERR_NOT_LOADED, "vq weights not loaded");
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");

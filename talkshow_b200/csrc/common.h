@@ -211,6 +211,13 @@ struct LoadScope {
 };
 }  // namespace ts
 
+namespace ts {
+// entry points that launch kernels: a host-only (planning) engine has no device and no device copies of its weights
+inline void require_device(const ts_engine* e) {
+  if (e->host_only) fail(TS_ERR_UNSUPPORTED, "host-only engine cannot execute");
+}
+}  // namespace ts
+
 // run `body`, convert exceptions to status codes
 #define TS_API_BEGIN(e) \
   try {                 \

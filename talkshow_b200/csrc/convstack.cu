@@ -287,6 +287,7 @@ extern "C" int ts_load_vq(ts_engine* e, int which, const ts_tensor* tensors, int
 
 extern "C" int ts_audio_encode(ts_engine* e, const float* mfcc, float* out, int B, int M, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (!e->conv || !e->conv->audio_loaded) fail(TS_ERR_NOT_LOADED, "audio encoder weights not loaded");
   if (B <= 0 || M < 4) fail(TS_ERR_INVALID, "ts_audio_encode: B=%d M=%d", B, M);
   cudaStream_t s = (cudaStream_t)stream;
@@ -301,6 +302,7 @@ extern "C" int ts_audio_encode(ts_engine* e, const float* mfcc, float* out, int 
 
 extern "C" int ts_vq_decode(ts_engine* e, int which, const int64_t* idx, float* out, int B, int T, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (which < 0 || which > 1 || !e->conv || !e->conv->vq[which].loaded) fail(TS_ERR_NOT_LOADED, "vq[%d] weights not loaded", which);
   if (B <= 0 || T <= 0) fail(TS_ERR_INVALID, "ts_vq_decode: B=%d T=%d", B, T);
   cudaStream_t s = (cudaStream_t)stream;
@@ -315,6 +317,7 @@ extern "C" int ts_vq_decode(ts_engine* e, int which, const int64_t* idx, float* 
 extern "C" int ts_vq_encode(ts_engine* e, int which, const float* poses, int64_t* idx, float* e_out, int B, int F,
                             void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (which < 0 || which > 1 || !e->conv || !e->conv->vq[which].loaded) fail(TS_ERR_NOT_LOADED, "vq[%d] weights not loaded", which);
   if (B <= 0 || F < 4) fail(TS_ERR_INVALID, "ts_vq_encode: B=%d F=%d", B, F);
   cudaStream_t s = (cudaStream_t)stream;

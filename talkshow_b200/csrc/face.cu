@@ -1437,6 +1437,7 @@ extern "C" int ts_load_face(ts_engine* e, const ts_tensor* tensors, int n) {
 
 extern "C" int ts_face_forward(ts_engine* e, const float* wave, const float* id, float* out, int B, int N, int frame, void* stream) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (!e->face) fail(TS_ERR_NOT_LOADED, "face weights not loaded");
   if (B <= 0 || N < 400 || frame <= 0) fail(TS_ERR_INVALID, "ts_face_forward: B=%d N=%d frame=%d (need >= 400 samples)", B, N, frame);
   cudaStream_t s = (cudaStream_t)stream;

@@ -1361,6 +1361,7 @@ extern "C" int64_t ts_pixelcnn_staged_row_bytes(ts_engine* e) {
 // CUDA-event timing of the persistent kernel on its launch stream (bench.py roofline leg).
 extern "C" int ts_pixelcnn_timing(ts_engine* e, int enable) {
   TS_API_BEGIN(e)
+  ts::require_device(e);
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
   PixelPlan* P = e->pix;
   if (enable && !P->ev0) {

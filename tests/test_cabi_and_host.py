@@ -59,6 +59,14 @@ def test_host_only_engine_rejects_execution_and_bad_checkpoints():
     assert e.L.ts_pixelcnn_plan_shape(e.h, C.byref(ns), C.byref(nc)) == 0 and (ns.value, nc.value) == (52, 148)
     with pytest.raises(RuntimeError, match="host-only"):
         e.pixelcnn_trace(0)
+    # every executing entry point refuses a planning engine before it touches a pointer (no device copies of the weights exist)
+    L, h, n = e.L, e.h, None
+    for name, args in (("ts_audio_encode", (h, n, n, 1, 8, n)), ("ts_vq_decode", (h, 0, n, n, 1, 2, n)), ("ts_vq_encode", (h, 0, n, n, n, 1, 8, n)),
+                       ("ts_face_forward", (h, n, n, n, 1, 16000, 30, n)), ("ts_body_generate", (h, n, n, n, n, n, 1, 8, n)),
+                       ("ts_assemble_pose", (h, n, n, n, 1, 4, 4, 0, n)), ("ts_rot6d_to_axis_angle", (h, n, n, 4, n)),
+                       ("ts_pixelcnn_generate", (h, n, n, n, n, n, 1, 2, n, 0, n)), ("ts_pixelcnn_timing", (h, 1)), ("ts_mfcc", (h, n, n, 1, 16000, 16000, n))):
+        assert getattr(L, name)(*args) != 0 and b"host-only" in L.ts_last_error(h), name
+    assert L.ts_set_vq_parallel(h, -1) != 0 and L.ts_set_vq_parallel(h, 16) == 0 and L.ts_set_pixelcnn_mode(h, 7) != 0
     with pytest.raises(ValueError):
         e.rot6d_to_axis_angle(torch.zeros(4, 5))
     e.close()
