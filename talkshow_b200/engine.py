@@ -128,8 +128,11 @@ class Engine:
         if p + "weight" not in sd:      # resolve the weight_norm parametrisation (dim=2), old or new names
             if p + "parametrizations.weight.original0" in sd:
                 g, v = sd.pop(p + "parametrizations.weight.original0"), sd.pop(p + "parametrizations.weight.original1")
-            else:
+            elif p + "weight_g" in sd and p + "weight_v" in sd:
                 g, v = sd.pop(p + "weight_g"), sd.pop(p + "weight_v")
+            else:
+                raise RuntimeError("ts_load_face: checkpoint tensor '%sweight' (or its weight_norm pair weight_g / weight_v, "
+                                   "parametrizations.weight.original0 / original1) missing" % p)
             sd[p + "weight"] = torch._weight_norm(v.float().cpu(), g.float().cpu(), 2)
         arr, keep = _lib.pack_tensors(sd)
         self._check(self.L.ts_load_face(self.h, arr, len(sd)), "ts_load_face")

@@ -51,6 +51,10 @@ def test_host_only_engine_rejects_execution_and_bad_checkpoints():
     bad["fusion_v.weight"] = torch.zeros(256, 256, 1, 1)
     with pytest.raises(RuntimeError, match="fusion_v.weight"):
         e.load_pixelcnn(bad)
+    with pytest.raises(RuntimeError, match="weight_norm"):
+        e.load_face({})
+    with pytest.raises(RuntimeError, match="embedding.weight"):
+        e.load_pixelcnn(synth.body_pixel_checkpoint(0)["audioencoder"])          # the wrong module's dict
     e.load_pixelcnn(sd)
     assert e.pixelcnn_row_bytes == 89774080
     assert e.pixelcnn_staged_row_bytes > e.pixelcnn_row_bytes
