@@ -215,6 +215,9 @@ extern "C" int ts_body_generate(ts_engine* e, const float* mfcc, const int64_t* 
   if (!e->conv || !e->conv->audio_loaded) fail(TS_ERR_NOT_LOADED, "audio encoder weights not loaded");
   if (!e->conv->vq[0].loaded || !e->conv->vq[1].loaded) fail(TS_ERR_NOT_LOADED, "vq weights not loaded");
   if (!e->pix) fail(TS_ERR_NOT_LOADED, "pixelcnn weights not loaded");
+  for (int w = 0; w < 2; ++w)   // the sampler emits indices in [0, 2048): F.embedding of the reference would raise on a smaller codebook
+    if (e->conv->vq[w].ncodes < PIX_NCODE)
+      fail(TS_ERR_INVALID, "ts_body_generate: vq[%d] codebook has %d codes, the PixelCNN samples %d", w, e->conv->vq[w].ncodes, PIX_NCODE);
   if (B <= 0 || M < 4) fail(TS_ERR_INVALID, "ts_body_generate: B=%d M=%d", B, M);
   cudaStream_t s = (cudaStream_t)stream;
   const int T = ts_latent_rows(M);
