@@ -84,7 +84,8 @@ int ts_pixelcnn_logits(ts_engine* e, const float* aud, const int64_t* label, con
                        float* logits_out, int B, int T, void* stream);
 
 /* VQVAE.decode(latents=...), nets/spg/vqvae_1d.py:201-208: idx [B,T] int64 -> out [B,C,4T]
- * (C = ts_vq_dim(which): 39 body / 90 hand, 78 / 180 for 6-D). */
+ * (C = ts_vq_dim(which): 39 body / 90 hand, 78 / 180 for 6-D).  The indices are device data and are NOT range-checked (the
+ * reference's F.embedding raises IndexError): every idx must lie in [0, num_embeddings) of the loaded codebook. */
 int ts_vq_decode(ts_engine* e, int which, const int64_t* idx, float* out, int B, int T, void* stream);
 /* VQVAE.encode, :196-199: poses [B,F,C] -> idx [B,T] int64 (T=F/4), e_out (may be NULL) [B,64,T]. */
 int ts_vq_encode(ts_engine* e, int which, const float* poses, int64_t* idx, float* e_out, int B, int F,
