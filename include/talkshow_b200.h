@@ -75,7 +75,9 @@ int ts_latent_rows(int M);
  * pre_latents is given, :158-165), label [B] int64, noise [2T,B,2048] = the Exp(1) draws the
  * reference's multinomial would consume, one [B,2048] block per sampled position in the order
  * (i,0),(i,1) (RNG contract), pre_latents [B,T0,2] int64 or NULL (T0=0).
- * idx_out [B,T,2] int64.  logits_out (may be NULL) [2T,B,2048]: the logits each draw used. */
+ * idx_out [B,T,2] int64.  logits_out (may be NULL) [2T,B,2048]: the logits each draw used.
+ * Device data is not range-checked: pre_latents (and `codes` of ts_pixelcnn_logits) must lie in [0,2048) like the
+ * indices nn.Embedding accepts; labels outside [0, num_classes) are clamped. */
 int ts_pixelcnn_generate(ts_engine* e, const float* aud, const int64_t* label, const float* noise,
                          int64_t* idx_out, float* logits_out, int B, int T, const int64_t* pre_latents, int T0,
                          void* stream);
