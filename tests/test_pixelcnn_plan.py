@@ -155,3 +155,21 @@ def test_plan_rejects_too_few_ctas(ckpts, level, ctas):
     with pytest.raises(RuntimeError, match="pixelcnn plan"):
         e.load_pixelcnn(ckpts["pixel"]["generator"])
     e.close()
+
+
+def test_default_plan_tables_are_pinned(ckpts):
+    """The stage tables of the plans the product runs by default (one CTA per SM, and the 96-CTA plan of the overlapped step) and of
+    the two cross-check plans: any change to the builder that moves a task shows up here before it reaches a GPU (the tables of
+    these four plans were the same before and after the round-2 builder changes; the kernels ran on exactly these)."""
+    import hashlib
+
+    want = {("fused", 0): "d7da3b16adf5", ("plain", 0): "b3d2b9c3c967", ("sched2", 0): "46eeee405bdc", ("fused", 96): "87f66d560666"}
+    for (name, ctas), digest in want.items():
+        e = Engine(-148)
+        e.set_pixelcnn_fusion({"plain": 0, "sched2": 2}.get(name, 1))
+        if ctas:
+            e.set_pixelcnn_ctas(ctas)
+        e.load_pixelcnn(ckpts["pixel"]["generator"])
+        table, _ = _lib.plan_to_numpy(e.h)
+        e.close()
+        assert hashlib.sha1(table.tobytes()).hexdigest()[:12] == digest, (name, ctas)
