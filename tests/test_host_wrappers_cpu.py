@@ -229,6 +229,28 @@ def test_demo_flow_on_the_oracle_engine(ckpts, tmp_path, monkeypatch, shared):
             torch.manual_seed(seed)
             res, _ = demo.infer(g_body, g_face, None, None, config, vargs, save=False)
             assert np.abs(res[0].numpy()[::3] - gold[key]).max() <= 1e-5, key
+    # the command-line entry point (scripts/demo.py:250-300 main): config file -> both wrappers from checkpoint files -> infer
+    import json
+    cfg_json = json.load(open(os.path.join(ROOT, "config", "body_pixel.json")))
+    cfg_json["Model"]["vq_path"] = str(tmp_path / "vq.pth")
+    json.dump(cfg_json, open(str(tmp_path / "cfg.json"), "w"))
+    import talkshow_b200.nets.base as base
+    monkeypatch.setattr(base, "resolve_device", lambda gpu: torch.device("cpu"))
+    for mod in ("smplx_body_pixel", "smplx_face"):
+        monkeypatch.setattr(__import__("talkshow_b200.nets." + mod, fromlist=["x"]), "resolve_device", base.resolve_device)
+    torch.manual_seed(seed)
+    orig_init = demo.init_model
+
+    def init_cpu_noise(name, path, a, c):
+        g = orig_init(name, path, a, c)
+        g.noise_device = "cpu"
+        return g
+
+    monkeypatch.setattr(demo, "init_model", init_cpu_noise)
+    main_list, main_verts = demo.main(["--config_file", str(tmp_path / "cfg.json"), "--infer", "--audio_file", wav, "--id", str(spk),
+                                       "--num_sample", str(nsamp), "--body_model_path", str(tmp_path / "body.pth"),
+                                       "--face_model_path", str(tmp_path / "face.pth")])
+    assert main_verts is None and all(torch.equal(a, b) for a, b in zip(main_list, result_list))
     # the pinned transformers (no torch draws in the face pass): forced by the attribute, differs from the auto mode exactly then
     g_face.layerdrop_rng_draws = 0
     torch.manual_seed(seed)
