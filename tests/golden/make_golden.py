@@ -358,6 +358,50 @@ def main():
                             **{k: (v[::5].copy() if isinstance(v, np.ndarray) else v) for k, v in fe.items()},
                             shapes=np.array([fe["ta_30"].shape[0], fe["ta_15"].shape[0], fe["sepa_30"].shape[0], fe["sepa_15"].shape[0]]))
         print("frontend", fe["ta_30"].shape, fe["gap_30"], fe["gap_15"])
+    # ---- SMPL-X call semantics: the reference's get_vertices (scripts/demo.py:122-152) and get_joints (data_utils/get_j.py:20-51)
+    #      run on a stand-in smplx_model that answers each per-frame keyword call with the float64 restatement of smplx 0.1.28
+    #      (oracle/smplx_oracle.py; the package and the licensed model file are absent).  Pins WHICH columns of the 265-vector the
+    #      reference hands to which argument, the per-frame loop and the output layouts — not the body model's arithmetic. ----
+    if want("smplx_calls"):
+        import importlib.machinery
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import smplx_oracle as SO
+        from talkshow_b200 import smplx_lbs
+        if "scripts.demo" not in sys.modules:
+            for name, attrs in (("visualise", {}), ("visualise.rendering", {"RenderTool": object})):
+                m = types.ModuleType(name)
+                m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+                m.__path__ = []
+                for k, v in attrs.items():
+                    setattr(m, k, v)
+                sys.modules[name] = m
+        import scripts.demo as ref_demo2
+        import data_utils.get_j as ref_getj
+        model = smplx_lbs.synthetic_model(V=300, seed=11, nfaces=500)
+
+        class _Model:
+            batch_size = 1
+            calls = 0
+
+            def __call__(self, betas=None, expression=None, jaw_pose=None, leye_pose=None, reye_pose=None, global_orient=None,
+                         body_pose=None, left_hand_pose=None, right_hand_pose=None, return_verts=True):
+                _Model.calls += 1
+                p = torch.cat([jaw_pose, leye_pose, reye_pose, global_orient, body_pose, left_hand_pose, right_hand_pose, expression], 1)
+                v, j = SO.smplx_forward(model, p, betas[:1])
+                out = {"vertices": v, "joints": j, "body_pose": body_pose}
+                return type("Out", (dict,), {"__getattr__": dict.__getitem__})(out)
+
+        gen = torch.Generator().manual_seed(12)
+        res = [((torch.rand(5, 265, generator=gen, dtype=torch.float64) * 2 - 1) * 0.4) for _ in range(2)]
+        betas = (torch.rand(1, 300, generator=gen, dtype=torch.float64) - 0.5) * 0.2
+        verts, poses = ref_demo2.get_vertices(_Model(), betas, [r.clone() for r in res], True, require_pose=True)
+        assert _Model.calls == 10                                   # one model call per frame
+        joints3 = ref_getj.get_joints(_Model(), betas, torch.stack(res).clone())        # [2,5,127,3]
+        joints2 = ref_getj.get_joints(_Model(), betas, res[0].clone())                  # [5,127,3]
+        np.savez_compressed(os.path.join(HERE, "smplx_calls.npz"), verts=np.stack(verts).astype(np.float32),
+                            poses=torch.stack(poses).numpy().astype(np.float32), joints3=joints3.numpy().astype(np.float32),
+                            joints2=joints2.numpy().astype(np.float32), model_seed=11, V=300, nfaces=500, pose_seed=12)
+        print("smplx_calls", np.stack(verts).shape, tuple(joints3.shape))
     # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
     if want("options"):
         import json

@@ -86,3 +86,43 @@ def test_smplx_forward_matches_oracle():
     finally:
         torch.cuda.synchronize()
         e.close()
+
+
+def test_host_mirror_matches_reference_call_semantics():
+    """get_vertices / get_joints / the keyword call of talkshow_b200.smplx_lbs against the reference's own get_vertices
+    (scripts/demo.py:122-152) and get_joints (data_utils/get_j.py:20-51), both answered by the same float64 restatement of the body
+    model (fixture: tests/golden/make_golden.py --only smplx_calls): which columns of the 265-vector feed which argument, one
+    batched call instead of one per frame, output layouts."""
+    import os
+
+    from conftest import GOLDEN
+
+    g = np.load(os.path.join(GOLDEN, "smplx_calls.npz"))
+    model = smplx_lbs.synthetic_model(V=int(g["V"]), seed=int(g["model_seed"]), nfaces=int(g["nfaces"]))
+
+    class Model(smplx_lbs.SmplxModel):                     # the engine call replaced by the oracle; everything else is the product's
+        def __init__(self):
+            self.device, self.batch_size, self.calls = torch.device("cpu"), 1, 0
+
+        def forward_pose265(self, pose265, betas=None, expression=True, want_vertices=True):
+            self.calls += 1
+            v, j = SO.smplx_forward(model, pose265, betas, use_expression=expression)
+            return (v if want_vertices else None), j
+
+    gen = torch.Generator().manual_seed(int(g["pose_seed"]))
+    res = [((torch.rand(5, 265, generator=gen, dtype=torch.float64) * 2 - 1) * 0.4) for _ in range(2)]
+    betas = (torch.rand(1, 300, generator=gen, dtype=torch.float64) - 0.5) * 0.2
+    m = Model()
+    verts, poses = smplx_lbs.get_vertices(m, betas, res, True, require_pose=True)
+    assert m.calls == 2                                    # one call per sample, not per frame
+    assert np.abs(np.stack(verts) - g["verts"]).max() <= 1e-6 and np.abs(torch.stack(poses).numpy() - g["poses"]).max() <= 1e-7
+    j3 = smplx_lbs.get_joints(m, betas, torch.stack(res))
+    j2 = smplx_lbs.get_joints(m, betas, res[0])
+    assert j3.shape == (2, 5, 127, 3) and j2.shape == (5, 127, 3)
+    assert np.abs(j3.numpy() - g["joints3"]).max() <= 1e-6 and np.abs(j2.numpy() - g["joints2"]).max() <= 1e-6
+    # the keyword call of the reference's smplx_model (demo.py:129-138), many frames at once
+    p = res[1]
+    out = m(betas=betas, expression=p[:, 165:265], jaw_pose=p[:, 0:3], leye_pose=p[:, 3:6], reye_pose=p[:, 6:9], global_orient=p[:, 9:12],
+            body_pose=p[:, 12:75], left_hand_pose=p[:, 75:120], right_hand_pose=p[:, 120:165], return_verts=True)
+    assert np.abs(out.vertices.numpy() - g["verts"][1]).max() <= 1e-5 and torch.equal(out.body_pose, p[:, 12:75])
+    assert np.abs(out["joints"].numpy() - g["joints3"][1]).max() <= 1e-5
