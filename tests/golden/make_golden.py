@@ -160,7 +160,8 @@ def main():
         gv.load_state_dict(vq_ckpt)
         poses = synth.synth_poses(2, 300, seed=313)
         outv = gv.infer_on_audio(torch.zeros(2, 64, 300), initial_pose=poses, continuity=True, fps=30)   # (300, 258)
-        np.savez_compressed(os.path.join(HERE, "wrapper_cont.npz"), pred=pred[:, ::3].copy(), pred_stride=3,
+        outs = gv.infer_on_audio(torch.zeros(1, 64, 300), initial_pose=synth.synth_poses(1, 300, seed=5), fps=30, smooth=True)    # (300, 129): :283-291
+        np.savez_compressed(os.path.join(HERE, "wrapper_cont.npz"), vq_smooth=outs[140:170].copy(), pred=pred[:, ::3].copy(), pred_stride=3,
                             pred_seam=pred[:, 52:68].copy(), label=np.array([2]),
                             noise_fp0=noise_fp(n0), noise_fp1=noise_fp(n1), sampler_seed=SAMPLER_SEED + 3,
                             vq_out=outv[::3].copy(), vq_seam=outv[56:64].copy())

@@ -152,6 +152,7 @@ def test_body_vq_wrapper_golden(ckpts, shared):
     base = g.infer_on_audio(None, initial_pose=synth.synth_poses(1, 300, seed=5), fps=30)
     sm = g.infer_on_audio(None, initial_pose=synth.synth_poses(1, 300, seed=5), fps=30, smooth=True)
     assert np.array_equal(sm[:149], base[:149]) and np.array_equal(sm[159:], base[159:]) and not np.array_equal(sm[149:159], base[149:159])
+    assert np.abs(sm[140:170] - gc["vq_smooth"]).max() <= 1e-5                  # the reference's smooth=True output around frame 149
 
 
 def test_face_wrapper_golden(ckpts, shared):
