@@ -8,6 +8,7 @@ import os
 import numpy as np
 import torch
 
+from ..data_utils.lower_body import c_index_3d, c_index_6d
 from ..data_utils.utils import get_mfcc_sepa, get_mfcc_ta, load_wav
 from .base import draw_sampler_noise, resolve_device, shared_engine, strip_module
 
@@ -32,6 +33,7 @@ class TrainWrapper:
         if not self.bh_model or not self.composition:
             raise NotImplementedError("talkshow_b200 builds the bh_model=true, composition=true prior "
                                       "(config/body_pixel.json); convert_to_6d selects the dim 512 x 10-layer geometry")
+        self.c_index = c_index_6d if self.convert_to_6d else c_index_3d      # :72-75
         self.engine = engine or shared_engine(self.device)
         self.noise_device = self.device      # 'cpu' reproduces the CPU reference's RNG stream
         self.noise_per_step = True

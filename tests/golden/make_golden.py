@@ -403,6 +403,18 @@ def main():
                             poses=torch.stack(poses).numpy().astype(np.float32), joints3=joints3.numpy().astype(np.float32),
                             joints2=joints2.numpy().astype(np.float32), model_seed=11, V=300, nfaces=500, pose_seed=12)
         print("smplx_calls", np.stack(verts).shape, tuple(joints3.shape))
+    # ---- pose layout helpers of data_utils/lower_body.py (imported by scripts/demo.py:24, diversity.py, test_body.py) ----------
+    if want("lower_body"):
+        import data_utils.lower_body as ref_lb
+        gen = torch.Generator().manual_seed(77)
+        pred = torch.rand(6, 232, generator=gen)
+        full = torch.rand(6, 265, generator=gen)
+        gt = torch.rand(4, 265, generator=gen)
+        np.savez_compressed(os.path.join(HERE, "lower_body.npz"), seed=77, c_index_3d=np.asarray(ref_lb.c_index_3d), c_index_6d=np.asarray(ref_lb.c_index_6d),
+                            part2full=ref_lb.part2full(pred).numpy(), part2full_stand=ref_lb.part2full(pred, True).numpy(),
+                            pred2poses=ref_lb.pred2poses(pred, gt).numpy(), poses2poses=ref_lb.poses2poses(full, gt).numpy(),
+                            poses2pred=ref_lb.poses2pred(full).numpy(), poses2pred_stand=ref_lb.poses2pred(full, True).numpy())
+        print("lower_body", len(ref_lb.c_index_3d), len(ref_lb.c_index_6d))
     # ---- CLI surface: trainer/options.py:3-37 (demo.py:251-252 does parse_args().parse_args()) ------------------
     if want("options"):
         import json

@@ -155,6 +155,20 @@ def test_pose_layout_matches_the_files_the_reference_ships():
     assert kinds == {"sit", "stand", "only_face"}
 
 
+def test_lower_body_helpers_match_reference():
+    """data_utils/lower_body.py of the reference, run on random inputs (tests/golden/make_golden.py --only lower_body): index tables and
+    the four layout functions, bit for bit."""
+    from talkshow_b200.data_utils import lower_body as lb
+
+    g = np.load(os.path.join(GOLDEN, "lower_body.npz"))
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    pred, full, gt = torch.rand(6, 232, generator=gen), torch.rand(6, 265, generator=gen), torch.rand(4, 265, generator=gen)
+    assert np.array_equal(lb.c_index_3d, g["c_index_3d"]) and np.array_equal(lb.c_index_6d, g["c_index_6d"])
+    for name, got in (("part2full", lb.part2full(pred)), ("part2full_stand", lb.part2full(pred, True)), ("pred2poses", lb.pred2poses(pred, gt)),
+                      ("poses2poses", lb.poses2poses(full, gt)), ("poses2pred", lb.poses2pred(full)), ("poses2pred_stand", lb.poses2pred(full, True))):
+        assert np.array_equal(got.numpy(), g[name]), name
+
+
 def test_shard_ranges_cover_batch():
     from talkshow_b200.pipeline import shard_range
 
